@@ -1,0 +1,220 @@
+"""Pin the CPU oracle: (1) against golden vectors produced by the reference's own files
+(tests/golden/make_golden.py), (2) against closed-form known-answer tests KAT-1..5."""
+import math
+
+import pytest
+import torch
+
+from oracle import volt_oracle as O
+
+
+def close(a, b, rtol=1e-5, atol=1e-7):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+# ------------------------------------------------------------------ goldens
+def test_golden_vol_kernel(golden):
+    g = golden["volk_1d"]
+    assert torch.equal(O.cum_trapz(g["vol"] * g["vol"], g["x"]), g["cumtrapz"])
+    assert torch.equal(O.vol_kernel(g["x"], g["vol"]), g["K"])
+    assert torch.equal(O.vol_kernel(g["x"], g["vol"], diag=True), g["diag"])
+    g = golden["volk_batched"]
+    assert torch.equal(O.vol_kernel(g["x"].unsqueeze(0).repeat(3, 1), g["vol"]), g["K"])
+    assert torch.equal(O.vol_kernel(g["x"], g["vol"]), g["K"])
+
+
+def test_golden_bm_kernel(golden):
+    g = golden["bmk"]
+    assert torch.equal(O.bm_vol_from_raw(g["raw_vol"]), g["vol"])
+    close(g["vol"], torch.tensor([0.2]))
+    assert torch.equal(O.bm_kernel(g["x1"], g["x1"], g["vol"]), g["K11"])
+    assert torch.equal(O.bm_kernel(g["x1"], g["x2"], g["vol"]), g["K12"])
+
+
+def test_golden_ewma(golden):
+    g = golden["ewma"]
+    for k in (5, 25, 100):
+        close(O.ewma(g["y"], k), g[f"k{k}"], rtol=1e-6, atol=1e-6)
+        close(O.ewma(g["yb"], k), g[f"kb{k}"], rtol=1e-6, atol=1e-6)
+        assert O.ewma(g["y"], k).shape == (65,)
+
+
+def test_golden_means(golden):
+    g = golden["means"]
+    tx, y, k = g["train_x"], g["train_y"], g["k"]
+    for kind, out in g["out"].items():
+        close(O.ma_mean_forward(kind, tx, y, k, tx, g["theta"]), out["train"], rtol=1e-6, atol=1e-6)
+        close(O.ma_mean_forward(kind, tx, y, k, tx[-1:] + 1.0, g["theta"]), out["one"], rtol=1e-6, atol=1e-6)
+        close(O.ma_mean_forward(kind, tx, y, k, torch.arange(65) / 252.0, g["theta"]), out["other"], rtol=1e-6, atol=1e-6)
+
+
+def test_golden_train_vol(golden):
+    g = golden["train_vol"]
+    out = O.train_vol_model(g["x"], g["vol"], train_iters=g["iters"])
+    close(out["raw_noise"], g["raw_noise"], rtol=1e-4, atol=1e-5)
+    close(out["raw_vol"], g["raw_vol"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma"])
+def test_golden_train_voltmagpie(golden, mean_func):
+    g = golden[f"train_volt_{mean_func}"]
+    assert g["requires_grad"] == [True, False, False]  # only the likelihood noise trains (train_utils.py:201-203)
+    assert g["param_names"][0] == "likelihood.noise_covar.raw_noise"
+    out = O.train_voltmagpie_model(g["x"], g["px"][1:], g["vol"], train_iters=g["iters"], k=g["k"], mean_func=mean_func)
+    close(out["raw_noise"], g["raw_noise"], rtol=1e-4, atol=1e-5)
+    logy = g["px"][1:].log()
+    mean = O.ma_mean_forward(mean_func, g["x"], logy, g["k"], g["x"])
+    loss = -O.exact_mll(O.vol_kernel(g["x"], g["vol"]), logy - mean, O.noise_from_raw(out["raw_noise"]))
+    close(loss.reshape(()), g["final_loss"].reshape(()), rtol=1e-4, atol=1e-6)
+
+
+def test_golden_mll_point(golden):
+    g = golden["mll_point"]
+    mean = O.ma_mean_forward("ewma", g["x"], g["logy"], g["k"], g["x"])
+    out = O.volt_mll_and_grad(g["x"], g["vol"], g["logy"] - mean, g["raw_noise"])
+    close(out["mll"].reshape(()), g["mll"].reshape(()), rtol=1e-4, atol=1e-6)
+    close(out["draw_noise"].reshape(1), g["draw_noise"].reshape(1), rtol=2e-3, atol=1e-5)
+
+
+def test_golden_bmgp_posterior(golden):
+    g = golden["bmgp_post"]
+    mean, cov = O.bmgp_posterior(g["train_x"], g["train_y"], g["test_x"], g["vol"], g["noise"])
+    close(mean, g["mean"], rtol=1e-4, atol=1e-5)
+    close(cov, g["cov"], rtol=1e-3, atol=1e-6)
+    close(O.mvn_sample(mean, cov, g["eps"]), g["samples"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma"])
+@pytest.mark.parametrize("th", ["none", "th"])
+def test_golden_rollouts(golden, mean_func, th):
+    g = golden[f"rollout_{mean_func}_{th}"]
+    out = O.rollouts(g["train_x"], g["train_y"], g["log_vol_path"], g["test_x"], g["pred_vol"], g["eps"],
+                     g["k"], mean_kind=mean_func, theta=g["theta"])
+    close(out, g["samples"], rtol=1e-5, atol=2e-5)
+
+
+def test_golden_genpred_step(golden):
+    g = golden["genpred_step"]
+    logy = g["train_y"][1:].log()
+    st = dict(train_x=g["train_x"], train_y=logy, log_vol_path=g["log_vol_path"], k=g["k"], mean_kind="ewma",
+              mean_train_x=g["train_x"], mean_train_y=logy)
+    s, _, _ = O.generate_prediction(st, g["test_x"], g["pred_vol"], g["eps"], g["latent_mean"], g["theta"])
+    close(s.reshape(-1), g["samples"].reshape(-1), rtol=1e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------ known-answer tests (fp64)
+def _rand_series(T, seed=0, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.arange(T, dtype=dtype) / 252.0
+    vol = (math.log(0.2) + 0.1 * torch.randn(T, generator=g, dtype=dtype)).exp()
+    return x, vol
+
+
+def test_kat1_kat2_structure():
+    """KAT-1 K == C diag(w sigma^2) C^T;  KAT-2 chol(K) == C diag(sqrt(w sigma^2)), logdet = sum log(w sigma^2)."""
+    T = 40
+    x, vol = _rand_series(T)
+    K = O.vol_kernel(x, vol)
+    w = (x[1] - x[0]) * torch.ones(T, dtype=x.dtype)
+    w[0] *= 0.5
+    w[-1] *= 0.5
+    d = w * vol * vol
+    C = torch.tril(torch.ones(T, T, dtype=x.dtype))
+    close(K, C @ torch.diag(d) @ C.T, rtol=1e-12, atol=1e-15)
+    L = torch.linalg.cholesky(K)
+    close(L, C @ torch.diag(d.sqrt()), rtol=1e-9, atol=1e-12)
+    close(2 * L.diagonal().log().sum(), d.log().sum(), rtol=1e-10, atol=0)
+
+
+def test_kat3_noise_free_predictor():
+    """KAT-3: K_tr^-1 K_tr,te = e_last; pred_var = dx/2 sigma_test^2; one rollout step = closed form."""
+    T, S, H, k = 32, 3, 4, 6
+    x, vol = _rand_series(T, 1)
+    g = torch.Generator().manual_seed(5)
+    px = (2.3 + 0.01 * torch.cumsum(torch.randn(T + 1, generator=g, dtype=torch.float64), 0)).exp()
+    test_x = torch.arange(H, dtype=torch.float64) / 252.0 + x[-1] + x[1]
+    pred_vol = vol[-1] * torch.exp(0.1 * torch.randn(S, H, generator=g, dtype=torch.float64))
+    eps = torch.randn(S, H, generator=g, dtype=torch.float64)
+    dense = O.rollouts(x, px, vol.log(), test_x, pred_vol, eps, k)
+    closed = O.rollout_closed_form(x, px, vol.log(), test_x, pred_vol, eps, k)
+    close(dense, closed, rtol=1e-7, atol=1e-8)
+    full_vol = torch.cat((vol, pred_vol[0, :1]))
+    Kf = O.vol_kernel(torch.cat((x, test_x[:1])), full_vol)
+    sol = torch.linalg.solve(Kf[:T, :T], Kf[:T, T:])
+    e_last = torch.zeros(T, 1, dtype=torch.float64)
+    e_last[-1] = 1
+    close(sol, e_last, rtol=0, atol=1e-8)
+    pv = Kf[T, T] - Kf[:T, T] @ sol[:, 0]
+    close(pv, 0.5 * (x[1] - x[0]) * pred_vol[0, 0] ** 2, rtol=1e-8, atol=1e-14)
+
+
+def test_kat4_gradients_match_autograd():
+    """Analytic dMLL/dnoise, dMLL/dresid against fp64 autograd through the Cholesky branch."""
+    T = 24
+    x, vol = _rand_series(T, 2)
+    g = torch.Generator().manual_seed(3)
+    r = 0.05 * torch.randn(T, generator=g, dtype=torch.float64)
+    for raw in (1e-5, -4.0):
+        raw_t = torch.tensor(raw, dtype=torch.float64, requires_grad=True)
+        r_t = r.clone().requires_grad_(True)
+        mll = O.exact_mll(O.vol_kernel(x, vol), r_t, O.noise_from_raw(raw_t))
+        g_raw, g_r = torch.autograd.grad(mll, [raw_t, r_t])
+        out = O.volt_mll_and_grad(x, vol, r, raw)
+        close(out["mll"], mll.detach(), rtol=1e-12, atol=0)
+        close(out["draw_noise"], g_raw, rtol=1e-9, atol=1e-14)
+        close(out["dresid"], g_r, rtol=1e-9, atol=1e-14)
+        # tr(A^-1) identity used by the CUDA path: dnoise = 1/2 (alpha.alpha - tr A^-1)/T
+        close(out["dnoise"], 0.5 * ((out["alpha"] ** 2).sum() - out["tr_inv"]) / T, rtol=1e-10, atol=1e-14)
+
+
+def test_kat4b_bm_scale_gradient_identity():
+    """For A = s K0 + noise I:  dMLL/ds = 1/2 [ (alpha.r - noise alpha.alpha) - (T - noise tr A^-1) ] / (s T)
+    -- the identity the CUDA BM path uses instead of a dense dK contraction."""
+    T = 20
+    x = torch.arange(1, T + 1, dtype=torch.float64) / 252.0
+    g = torch.Generator().manual_seed(4)
+    r = torch.randn(T, generator=g, dtype=torch.float64)
+    s = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    noise = torch.tensor(0.05, dtype=torch.float64)
+    mll = O.exact_mll(O.bm_kernel(x, x, s), r, noise)
+    (gs,) = torch.autograd.grad(mll, [s])
+    out = O.exact_mll_and_grad(O.bm_kernel(x, x, s.detach()), r, noise)
+    a = out["alpha"]
+    ident = 0.5 * ((a @ r - noise * (a @ a)) - (T - noise * out["tr_inv"])) / (s.detach() * T)
+    close(ident, gs, rtol=1e-9, atol=1e-14)
+
+
+def test_kat5_constant_vol_is_brownian():
+    """Constant sigma: VolatilityKernel == sigma^2 * BM kernel on the grid shifted by dx/2 (trapezoid end weights)."""
+    T = 16
+    x = torch.arange(T, dtype=torch.float64) / 252.0
+    sig = 0.3
+    K = O.vol_kernel(x, sig * torch.ones(T, dtype=torch.float64))
+    dx = x[1] - x[0]
+    xs = x + 0.5 * dx
+    xs[-1] -= 0.5 * dx
+    want = sig ** 2 * torch.minimum(xs[:, None], xs[None, :])
+    want[-1, -1] = sig ** 2 * (x[-1])
+    close(K, want, rtol=1e-12, atol=1e-15)
+
+
+def test_psd_safe_cholesky_policy():
+    A = torch.eye(4).repeat(3, 1, 1)
+    A[1, 0, 0] = 0.0  # exactly singular leading pivot -> fails, others untouched
+    with pytest.warns(RuntimeWarning):
+        L, added = O.psd_safe_cholesky(A, jitter=1e-4, return_jitter=True)
+    assert added.tolist() == pytest.approx([0.0, 1e-4, 0.0])
+    close(L[1, 0, 0], torch.tensor(1e-2), rtol=1e-5, atol=0)
+    close(L[0], torch.eye(4))
+    bad = -torch.eye(3)
+    with pytest.raises(O.NotPSDError):
+        with pytest.warns(RuntimeWarning):
+            O.psd_safe_cholesky(bad, jitter=1e-4)
+
+
+def test_synth_series_shapes():
+    x, vol, logy = O.synth_series(3, 64)
+    assert x.shape == (64,) and vol.shape == (3, 64) and logy.shape == (3, 64)
+    assert torch.all(vol > 0) and abs(float(logy[0, 0]) - math.log(10.0)) < 1e-6
+    x2, vol2, _ = O.synth_series(3, 64)
+    assert torch.equal(vol, vol2)
