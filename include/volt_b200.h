@@ -1,0 +1,161 @@
+/* volt_b200 -- C ABI of the B200-native Volt GP hot path (libvolt_b200.so).
+ *
+ * The reference (g-benton/Volt) has no FFI: its boundary for this path is a set of Python callables that
+ * delegate to torch / GPyTorch.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference repository root).  The Python host layer (volt_b200/*.py) binds these
+ * with ctypes and re-creates the voltron.* API on top; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All `const float*` / `float*` / `int*` arguments are DEVICE pointers unless the
+ *     function name ends in `_host`, in which case they are HOST pointers and the call performs the
+ *     host<->device copies itself and synchronises before returning.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer entry points only
+ *     enqueue work; they never synchronise.
+ *   - row-major, contiguous, float32 (the reference's precision).  Batched arrays put the series index first.
+ *   - return value: 0 on success, <0 on error (VOLT_ERR_*); volt_last_error() returns the message.
+ *     Numerical failure (matrix not positive definite) is NOT an error return: it is reported per matrix in `info`
+ *     exactly like torch.linalg.cholesky_ex (1-based order of the first non-positive leading minor, 0 = success).
+ *   - requires an sm_100 device; there is no CPU fallback.
+ */
+#ifndef VOLT_B200_H_
+#define VOLT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOLT_ABI_VERSION 1
+
+#define VOLT_OK 0
+#define VOLT_ERR_ARG (-1)
+#define VOLT_ERR_CUDA (-2)
+#define VOLT_ERR_ARCH (-3)
+#define VOLT_ERR_ALLOC (-4)
+
+/* number of floats per series in the `scalars` output of the MLL entry points */
+#define VOLT_NSCALARS 16
+/* scalars[b*16 + i]: */
+#define VOLT_S_MLL 0       /* -1/2 (r^T A^-1 r + logdet A + T log 2pi) / T   (GPyTorch ExactMarginalLogLikelihood) */
+#define VOLT_S_DNOISE 1    /* d MLL / d noise = 1/2 (alpha.alpha - tr A^-1) / T                                     */
+#define VOLT_S_LOGDET 2
+#define VOLT_S_INVQUAD 3
+#define VOLT_S_TRINV 4     /* tr(A^-1) = ||L^-1||_F^2 */
+#define VOLT_S_ALAL 5      /* alpha.alpha, alpha = A^-1 r; d MLL / d r = -alpha / T */
+#define VOLT_S_ALR 6       /* alpha.r */
+#define VOLT_S_JITTER 7    /* jitter the psd_safe_cholesky policy had to add (0 if none) */
+#define VOLT_S_Z2Z2 8      /* |L^-1 rhs2|^2   (second right-hand side, used by the rollout) */
+#define VOLT_S_Z1Z2 9      /* (L^-1 r).(L^-1 rhs2) */
+
+/* moving-average mean families (voltron/means/EWMA.py) */
+#define VOLT_MA_EWMA 0
+#define VOLT_MA_DEWMA 1
+#define VOLT_MA_TEWMA 2
+#define VOLT_MA_MEANREVERT 3
+#define VOLT_MA_GIVEN 4    /* parametric mean evaluated by the caller (constant / linear / log-linear) */
+
+/* input encodings of a volatility path */
+#define VOLT_VOL_SIGMA 1      /* sigma      -> integrand sigma^2            */
+#define VOLT_VOL_LOGSIGMA 2   /* log sigma  -> integrand exp(log sigma)^2   (model.log_vol_path.exp(), rollout_utils.py:7) */
+#define VOLT_VOL_RAW 0        /* integrand given directly (CumTrapz(y, x))  */
+
+const char* volt_last_error(void);
+int volt_abi_version(void);
+/* 0 if the current CUDA device is sm_100 (B200); VOLT_ERR_ARCH otherwise. */
+int volt_device_check(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches counter) */
+long long volt_launch_count(void);
+
+/* CumTrapz(y, x)  -- voltron/kernels/VolKernel.py:4-10.
+ * x (T) or (B,T) if x_batched; y (B,T) encoded per `vol_mode`; half_last=1 reproduces the reference weights
+ * dx*[1/2,1,...,1,1/2]; half_last=0 keeps the last weight at dx (prefix of a longer grid, used by the rollout). */
+int volt_cumtrapz(const float* x, int x_batched, const float* y, int B, int T, int vol_mode, int half_last, float* V,
+                  void* stream);
+
+/* VolatilityKernel.forward(x, vol_path)  -- voltron/kernels/VolKernel.py:18-41.
+ * K[b,i,j] = V[b,min(i,j)] (+ add_diag[b*add_stride] on the diagonal when add_diag != NULL, the likelihood noise of
+ * [GPyTorch] GaussianLikelihood.__call__).  K is (B,T,T). */
+int volt_vol_cov(const float* x, int x_batched, const float* vol, int vol_mode, int B, int T, const float* add_diag,
+                 int add_stride, float* K, void* stream);
+
+/* BMKernel.forward(x1, x2)  -- voltron/kernels/BMKernel.py:38-51.  K[i,j] = vol[0] * min(x1_i, x2_j), K is (n1,n2). */
+int volt_bm_cov(const float* x1, int n1, const float* x2, int n2, const float* vol, float* K, void* stream);
+
+/* EWMA(y, k)  -- voltron/means/EWMA.py:20-37.  y (S,T) -> out (S,T+1). */
+int volt_ewma(const float* y, int S, int T, int k, float* out, void* stream);
+
+/* EWMAMean / DEWMAMean / TEWMAMean / MeanRevertingEMAMean full-length paths  -- voltron/means/EWMA.py:39-135.
+ * y (S,T) -> out (S,T+1).  Optional outputs (NULL to skip): e_out, ee_out (S,T+1) intermediate EWMA paths,
+ * resid_out (S,T) = y - out[:, :T] (the training residual y - mean_module(train_x)).
+ * latent (S): MeanRevertingEMAMean.latent_mean, only read for VOLT_MA_MEANREVERT. */
+int volt_ma_mean(const float* y, int S, int T, int k, int kind, float theta, const float* latent, float* out, float* e_out,
+                 float* ee_out, float* resid_out, void* stream);
+
+/* One exact MLL + gradient evaluation per series for the data model (Volatility kernel):
+ *   loss = -mll(model(train_x), y); loss.backward()   -- voltron/train_utils.py:247-250 (and :134-137),
+ *   [GPyTorch] ExactMarginalLogLikelihood / MultivariateNormal.log_prob / psd_safe_cholesky.
+ * A_b = K(x, vol_b) + noise_b I is generated inside the factorisation (never written to HBM).
+ * resid (B,T) = y - mean; noise (B) with stride noise_stride (0 = shared scalar).
+ * jitter / max_tries: psd_safe_cholesky policy (GPyTorch default 1e-6 / 3); jitter <= 0 disables the retry.
+ * Outputs: scalars (B,VOLT_NSCALARS), alpha (B,T) or NULL, info (B) or NULL. */
+int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* noise,
+                      int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                      void* stream);
+
+/* Same for the vol model BMGP (A = scale_b * min(x_i, x_j) + noise_b I)  -- voltron/train_utils.py:86-90,
+ * voltron/models/BMGP.py:20-28.  x (T) shared grid. */
+int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise,
+                     int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                     void* stream);
+
+/* Same for an explicit dense covariance K (B,T,ld) (lower triangle read) + noise_b I  -- the generic
+ * MultivariateNormal.log_prob path used when a caller hands over an evaluated kernel matrix. */
+int volt_mll_grad_dense(const float* K, long long k_bstride, int ld, const float* resid, const float* noise, int noise_stride,
+                        int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, void* stream);
+
+/* Host-buffer variant of volt_mll_grad_vol (all pointers are HOST memory; pinned memory recommended). */
+int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid, const float* noise, int noise_stride, int B,
+                           int T, float jitter, int max_tries, float* scalars, float* alpha, int* info);
+
+/* psd_safe_cholesky(A, jitter) / torch.linalg.cholesky_ex  -- voltron/rollout_utils.py:35,46; VoltMagpie.py:87,92.
+ * A (B,T,lda) lower triangle read (+ add_diag); L (B,T,ldl) lower factor, strict upper triangle zeroed.
+ * jitter_used (B) or NULL. */
+int volt_potrf(const float* A, long long a_bstride, int lda, const float* add_diag, int add_stride, int B, int T, float jitter,
+               int max_tries, float* L, long long l_bstride, int ldl, float* jitter_used, int* info, void* stream);
+
+/* torch.cholesky_solve(rhs, L)  -- voltron/rollout_utils.py:36,44.  rhs (B,T,nrhs) overwritten with the solution;
+ * forward_only=1 stops after L^-1 rhs. */
+int volt_potrs(const float* L, long long l_bstride, int ldl, int B, int T, float* rhs, long long r_bstride, int nrhs,
+               int forward_only, void* stream);
+
+/* BMGP in eval mode: model.vol_model(test_x)  -- voltron/rollout_utils.py:66, voltron/models/BMGP.py:18-28,
+ * [GPyTorch] ExactGP.__call__ / DefaultPredictionStrategy.  x (T), y (B,T) = log vol, xs (H).
+ * Outputs mean (B,H), cov (B,H,H), info (B). */
+int volt_bmgp_posterior(const float* x, const float* y, int B, int T, const float* xs, int H, const float* vol, int vol_stride,
+                        const float* noise, int noise_stride, float* mean, float* cov, int* info, void* stream);
+
+/* MultivariateNormal.sample(): samples[b,s,:] = mean[b] + psd_safe_cholesky(cov[b]) eps[b,:,s]; eps is (B,H,S).
+ * exp_out=1 applies exp() (pred_vol = ...sample(...).exp(), rollout_utils.py:66). */
+int volt_mvn_sample(const float* mean, const float* cov, const float* eps, int B, int H, int S, float jitter, int exp_out,
+                    float* samples, int* info, void* stream);
+
+/* GeneratePrediction + Rollouts  -- voltron/rollout_utils.py:6-93 (joint=0), and the multi-point draw of
+ * rollout_utils.py:6-53 / voltron/models/VoltMagpie.py:67-99 (joint=1).
+ *   x (n) training grid (uniform; only dx = x[1]-x[0] enters, as in CumTrapz), logy (B,n) log prices on that grid,
+ *   vol (B,n) volatility path encoded per vol_mode, pred_vol (B,S,H) sigma draws for the H test points,
+ *   eps (B,S,H) base normals or NULL (in-kernel Philox seeded by `seed`),
+ *   mean_kind: VOLT_MA_* ; k window; mr_theta / mr_latent (B): MeanRevertingEMAMean parameters;
+ *   resid_given (B,n), mean_test (B,H): required for VOLT_MA_GIVEN (y - mean(train_x), mean(test_x));
+ *   use_theta / theta / latent (B): the rollout-level mean reversion of rollout_utils.py:41-42;
+ *   jitter: psd_safe_cholesky jitter (1e-4 in rollout_utils.py:35,46; 1e-6 in VoltMagpie.py:87,92).
+ * Outputs samples (B,S,H) log prices; draw_info (B,S) bit flags (1: non-positive pivot in the per-draw rows,
+ * 2: pred_cov needed jitter, 4: pred_cov not PSD after 3 tries); series_info (B) cholesky_ex info of the shared block. */
+int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mode, const float* pred_vol, const float* eps,
+                 int B, int n, int S, int H, int mean_kind, int k, float mr_theta, const float* mr_latent,
+                 const float* resid_given, const float* mean_test, int use_theta, float theta, const float* latent, int joint,
+                 float jitter, unsigned long long seed, float* samples, int* draw_info, int* series_info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLT_B200_H_ */

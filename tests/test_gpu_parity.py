@@ -1,0 +1,386 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every test drives the CUDA path through the C ABI
+(ctypes wrappers in volt_b200.ops / the voltron mirror) and compares with the CPU oracle on the same seeded inputs,
+with the committed golden vectors produced by the reference's own files, and -- at BASELINE.json's full sizes --
+through size-independent properties.
+
+Tolerances (north_star): bit-exact for the gathered covariance; 1e-4 relative on the MLL; 1e-3 relative on posterior
+means / samples; gradients 2e-3 relative."""
+import math
+import warnings
+
+import pytest
+import torch
+
+from oracle import volt_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import volt_b200
+
+    volt_b200._lib.require_device()
+    return volt_b200
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64).cpu(), torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ covariance build
+def test_library_loaded_and_arch(vb):
+    assert vb._lib.load().volt_abi_version() == 1
+    assert vb._lib.load().volt_device_check() == 0
+
+
+def test_vol_cov_golden_bit_exact(vb, golden):
+    g = golden["volk_1d"]
+    assert torch.equal(vb.ops.vol_cov(g["x"], g["vol"]), g["K"])
+    assert torch.equal(vb.CumTrapz(g["vol"] * g["vol"], g["x"]), g["cumtrapz"])
+    k = vb.VolatilityKernel()
+    assert torch.equal(k(g["x"], g["vol"]).evaluate(), g["K"])
+    assert torch.equal(k(g["x"], g["vol"], diag=True), g["diag"])
+    g = golden["volk_batched"]
+    assert torch.equal(k(g["x"].unsqueeze(0).repeat(3, 1).unsqueeze(-1), g["vol"].unsqueeze(-1)).evaluate(), g["K"])
+
+
+@pytest.mark.parametrize("B,T", [(1, 2), (3, 5), (2, 64), (5, 257), (2, 1000), (1, 4096)])
+def test_vol_cov_vs_oracle(vb, B, T):
+    x, vol, _ = O.synth_series(B, T)
+    K = vb.ops.vol_cov(x.cuda(), vol.cuda()).cpu()
+    assert torch.equal(K, O.vol_kernel(x, vol))
+    noise = torch.rand(B) + 0.1
+    Kn = vb.ops.vol_cov(x.cuda(), vol.cuda(), add_diag=noise.cuda()).cpu()
+    want = O.vol_kernel(x, vol) + noise[:, None, None] * torch.eye(T)
+    assert torch.equal(Kn, want)
+
+
+def test_bm_cov_golden(vb, golden):
+    g = golden["bmk"]
+    assert torch.equal(vb.ops.bm_cov(g["x1"], g["x1"], g["vol"]), g["K11"])
+    assert torch.equal(vb.ops.bm_cov(g["x1"], g["x2"], g["vol"]), g["K12"])
+    k = vb.BMKernel()
+    assert torch.allclose(k.vol.detach(), g["vol"], rtol=1e-6, atol=0)
+    assert torch.allclose(k(g["x1"], g["x2"]).evaluate().detach(), g["K12"], rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ moving averages
+def test_ewma_golden(vb, golden):
+    g = golden["ewma"]
+    for k in (5, 25, 100):
+        torch.testing.assert_close(vb.ops.ewma(g["y"], k), g[f"k{k}"], rtol=2e-6, atol=2e-6)
+        torch.testing.assert_close(vb.ops.ewma(g["yb"], k), g[f"kb{k}"], rtol=2e-6, atol=2e-6)
+
+
+def test_ma_means_golden(vb, golden):
+    g = golden["means"]
+    tx, y, k = g["train_x"], g["train_y"], g["k"]
+    classes = dict(ewma=vb.EWMAMean, dewma=vb.DEWMAMean, tewma=vb.TEWMAMean, meanrevert=vb.MeanRevertingEMAMean)
+    for kind, out in g["out"].items():
+        m = classes[kind](tx, y, k)
+        torch.testing.assert_close(m(tx), out["train"], rtol=5e-6, atol=5e-6)
+        torch.testing.assert_close(m(tx[-1:] + 1.0), out["one"], rtol=5e-6, atol=5e-6)
+        torch.testing.assert_close(m(torch.arange(65) / 252.0), out["other"], rtol=5e-6, atol=5e-6)
+
+
+@pytest.mark.parametrize("kind", ["ewma", "dewma", "tewma", "meanrevert"])
+@pytest.mark.parametrize("T,k", [(7, 25), (300, 25), (512, 100)])
+def test_ma_means_vs_oracle(vb, kind, T, k):
+    _, _, logy = O.synth_series(3, T)
+    for b in range(3):
+        want = O.ma_mean(kind, logy[b], k, theta=0.3)
+        got = vb.ops.ma_mean(kind, logy[b], k, theta=0.3, latent=logy[b].mean())
+        torch.testing.assert_close(got, want, rtol=5e-6, atol=5e-6)
+
+
+# ------------------------------------------------------------------------------------------------ exact MLL + grad
+@pytest.mark.parametrize("T", [2, 17, 48, 64, 65, 100, 128, 200, 256, 399, 512])
+def test_mll_grad_vol_vs_oracle(vb, T):
+    B, k = 3, 10
+    x, vol, logy = O.synth_series(B, T)
+    raw = torch.tensor([1e-5, -4.0, 1.0])
+    resid = torch.stack([logy[b] - O.ma_mean_forward("ewma", x, logy[b], k, x) for b in range(B)])
+    out = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid.cuda(), raw.cuda(), check=True)
+    for b in range(B):
+        ref = O.volt_mll_and_grad(x.double(), vol[b].double(), resid[b].double(), raw[b].double())
+        assert relerr(out["mll"][b], ref["mll"]) < 1e-4
+        assert relerr(out["draw_noise"][b], ref["draw_noise"]) < 2e-3
+        assert relerr(out["alpha"][b], ref["alpha"]) < 2e-3
+        assert relerr(out["scalars"][b, 2], ref["logdet"]) < 1e-4
+        assert relerr(out["scalars"][b, 4], ref["tr_inv"]) < 1e-3
+        ref32 = O.volt_mll_and_grad(x, vol[b], resid[b], raw[b])
+        assert relerr(out["mll"][b], ref32["mll"]) < 1e-4
+
+
+def test_mll_golden_point(vb, golden):
+    g = golden["mll_point"]
+    mean = vb.EWMAMean(g["x"], g["logy"], g["k"])(g["x"])
+    raw = g["raw_noise"].clone().requires_grad_(True)
+    noise = torch.nn.functional.softplus(raw) + 1e-4
+    mll = vb.ops.exact_mll("vol", g["x"], g["vol"], g["logy"] - mean, noise)
+    mll.backward()
+    assert relerr(mll.detach(), g["mll"]) < 1e-4
+    assert relerr(raw.grad, g["draw_noise"]) < 2e-3
+
+
+def test_mll_batch_equals_loop_and_replication(vb):
+    """P1 property tests: a batch equals the loop over its members; replicating a series leaves it unchanged."""
+    B, T = 5, 192
+    x, vol, logy = O.synth_series(B, T, seed=77)
+    resid = logy - logy.mean(-1, keepdim=True)
+    raw = torch.linspace(-3, 1, B)
+    full = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid.cuda(), raw.cuda())
+    for b in range(B):
+        one = vb.batched.mll_and_grad(x.cuda(), vol[b:b + 1].cuda(), resid[b:b + 1].cuda(), raw[b:b + 1].cuda())
+        assert torch.equal(one["mll"], full["mll"][b:b + 1])
+        assert torch.equal(one["alpha"], full["alpha"][b:b + 1])
+    rep = vb.batched.mll_and_grad(x.cuda(), vol[:1].repeat(300, 1).cuda(), resid[:1].repeat(300, 1).cuda(),
+                                  raw[:1].repeat(300).cuda())
+    assert bool((rep["mll"] == full["mll"][0]).all())
+
+
+def test_mll_bm_vs_oracle_autograd(vb):
+    T = 150
+    x = torch.arange(T) / 252.0
+    g = torch.Generator().manual_seed(3)
+    y = math.log(0.2) + torch.cumsum(0.08 * torch.randn(T, generator=g), 0)
+    for rv, rn in ((-1.3862944, 0.0), (-2.0, -3.0)):
+        ref = O.bm_mll_and_grad(x.double(), y.double(), torch.tensor([rv]).double(), torch.tensor([rn]).double())
+        raw_vol = torch.tensor([rv], requires_grad=True)
+        raw_noise = torch.tensor([rn], requires_grad=True)
+        vol = torch.sigmoid(raw_vol)
+        noise = torch.nn.functional.softplus(raw_noise) + 1e-4
+        mll = vb.ops.exact_mll("bm", x, vol, y - (-0.5 * vol.pow(2.0) * x), noise)
+        mll.backward()
+        assert relerr(mll.detach(), ref["mll"]) < 1e-4
+        assert relerr(raw_noise.grad, ref["draw_noise"]) < 2e-3
+        assert relerr(raw_vol.grad, ref["draw_vol"]) < 2e-3
+
+
+def test_mll_dense_matches_fused(vb):
+    B, T = 2, 130
+    x, vol, logy = O.synth_series(B, T, seed=5)
+    resid = logy - logy.mean(-1, keepdim=True)
+    noise = torch.tensor([0.05, 0.7])
+    K = O.vol_kernel(x, vol)
+    a = vb.ops.mll_grad("dense", None, K.cuda(), resid.cuda(), noise.cuda())
+    b = vb.ops.mll_grad("vol", x.cuda(), vol.cuda(), resid.cuda(), noise.cuda())
+    assert torch.equal(a["scalars"][:, :7], b["scalars"][:, :7])
+
+
+# ------------------------------------------------------------------------------------------------ Cholesky utilities
+@pytest.mark.parametrize("T", [1, 5, 64, 100, 300])
+def test_potrf_potrs_vs_torch(vb, T):
+    g = torch.Generator().manual_seed(T)
+    M = torch.randn(4, T, T, generator=g, dtype=torch.float64)
+    A = (M @ M.transpose(-1, -2) / T + torch.eye(T, dtype=torch.float64)).float()
+    L, info, ju = vb.ops.potrf(A.cuda())
+    assert int(info.abs().sum()) == 0 and float(ju.abs().sum()) == 0
+    want = torch.linalg.cholesky(A.double())
+    assert relerr(L, want) < 2e-5
+    assert float(L.cpu().triu(1).abs().max()) == 0.0
+    rhs = torch.randn(4, T, 3, generator=g)
+    sol = vb.ops.potrs(L, rhs.cuda())
+    assert relerr(sol, torch.cholesky_solve(rhs.double(), want)) < 1e-3
+
+
+def test_psd_safe_cholesky_policy(vb):
+    """Same engineered cases as the oracle's policy test: jitter only on the failing member, escalation, NotPSD."""
+    A = torch.eye(4).repeat(3, 1, 1)
+    A[1, 0, 0] = 0.0
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        L, info, ju = vb.ops.potrf(A, jitter=1e-4)
+    assert [round(float(v), 8) for v in ju] == [0.0, 1e-4, 0.0]
+    assert any("jitter" in str(x.message) for x in w)
+    assert abs(float(L[1, 0, 0]) - 1e-2) < 1e-6
+    assert torch.equal(L[0], torch.eye(4))
+    Lo, _ = O.psd_safe_cholesky(A, jitter=1e-4, return_jitter=True)
+    torch.testing.assert_close(L, Lo, rtol=1e-6, atol=1e-7)
+    with pytest.raises(vb.ops.NotPSDError):
+        vb.ops.potrf(-torch.eye(3), jitter=1e-4)
+    # info = order of the first non-positive leading minor (cholesky_ex convention), no retry when jitter <= 0
+    bad = torch.eye(70)
+    bad[66, 66] = -1.0
+    _, info, _ = vb.ops.potrf(bad, jitter=0.0, check=False)
+    _, info_t = torch.linalg.cholesky_ex(bad)
+    assert int(info[0]) == int(info_t) == 67
+
+
+# ------------------------------------------------------------------------------------------------ vol-model posterior
+def test_bmgp_posterior_golden(vb, golden):
+    g = golden["bmgp_post"]
+    mean, cov = vb.ops.bmgp_posterior(g["train_x"], g["train_y"], g["test_x"], g["vol"], g["noise"])
+    assert relerr(mean[0], g["mean"]) < 1e-3
+    assert relerr(cov[0], g["cov"]) < 2e-3
+    s = vb.ops.mvn_sample(g["mean"], g["cov"], g["eps"])
+    assert relerr(s[0], g["samples"]) < 1e-3
+
+
+def test_train_vol_model_golden(vb, golden):
+    g = golden["train_vol"]
+    torch.manual_seed(11)
+    vmod, vlh = vb.TrainVolModel(g["x"], g["vol"], train_iters=g["iters"])
+    torch.testing.assert_close(vlh.raw_noise.detach(), g["raw_noise"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(vmod.covar_module.raw_vol.detach(), g["raw_vol"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma"])
+def test_train_voltmagpie_golden(vb, golden, mean_func):
+    g = golden[f"train_volt_{mean_func}"]
+    vmod, vlh = vb.TrainVolModel(g["x"], g["vol"], train_iters=0)
+    volt, lh = vb.TrainVoltMagpieModel(g["x"], g["px"][1:], vmod, vlh, g["vol"], train_iters=g["iters"], k=g["k"],
+                                       mean_func=mean_func)
+    assert [n for n, _ in volt.named_parameters()] == g["param_names"]
+    assert [p.requires_grad for p in volt.parameters()] == g["requires_grad"]
+    torch.testing.assert_close(lh.raw_noise.detach(), g["raw_noise"], rtol=1e-3, atol=1e-4)
+    mll = vb.gp.ExactMarginalLogLikelihood(lh, volt)
+    loss = -mll(volt(g["x"]), g["px"][1:].log())
+    assert relerr(loss.detach(), g["final_loss"]) < 1e-4
+
+
+@pytest.mark.parametrize("mean_func", ["constant", "loglinear"])
+def test_train_parametric_means_golden(vb, golden, mean_func):
+    g = golden[f"genpred_multi_{mean_func}"]
+    vmod, vlh = vb.TrainVolModel(g["train_x"], g["vol"], train_iters=0)
+    torch.manual_seed(9)
+    volt, lh = vb.TrainVoltMagpieModel(g["train_x"], g["train_y"][1:], vmod, vlh, g["vol"], train_iters=g["iters"], k=g["k"],
+                                       mean_func=mean_func)
+    assert [n for n, _ in volt.named_parameters()] == g["param_names"]
+    assert [p.requires_grad for p in volt.parameters()] == g["requires_grad"]
+    torch.testing.assert_close(lh.raw_noise.detach(), g["raw_noise"], rtol=2e-3, atol=2e-4)
+    for n, p in volt.mean_module.named_parameters():
+        torch.testing.assert_close(p.detach(), g["mean_params"][n], rtol=2e-3, atol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------ rollouts
+@pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma"])
+@pytest.mark.parametrize("th", ["none", "th"])
+def test_rollout_golden(vb, golden, mean_func, th):
+    g = golden[f"rollout_{mean_func}_{th}"]
+    S, H = g["pred_vol"].shape
+    lat = None if g["theta"] is None else g["train_y"].log().mean()
+    out, dinfo, sinfo = vb.ops.rollout(g["train_x"], g["train_y"][1:].log(), g["log_vol_path"], g["pred_vol"].reshape(1, S, H),
+                                       eps=g["eps"].reshape(1, S, H), mean_kind=mean_func, k=g["k"], theta=g["theta"],
+                                       latent=lat, vol_mode=vb.ops.VOL_LOGSIGMA)
+    assert int(sinfo.sum()) == 0 and int((dinfo & 5).sum()) == 0
+    assert relerr(out[0], g["samples"]) < 1e-3
+
+
+def test_generate_prediction_step_golden(vb, golden):
+    g = golden["genpred_step"]
+
+    class M:
+        pass
+
+    m = M()
+    logy = g["train_y"][1:].log()
+    m.train_x, m.train_y, m.log_vol_path = g["train_x"], logy, g["log_vol_path"]
+    m.mean_module = vb.EWMAMean(g["train_x"], logy, g["k"])
+    from volt_b200.rollout_utils import _generate_prediction
+
+    out = _generate_prediction(m, g["test_x"], g["pred_vol"], g["eps"].reshape(6, 1), g["latent_mean"], g["theta"], 1e-4,
+                               m.train_x, m.train_y, m.log_vol_path)
+    assert relerr(out.reshape(-1), g["samples"].reshape(-1)) < 1e-3
+
+
+@pytest.mark.parametrize("mean_func", ["constant", "loglinear"])
+def test_generate_prediction_multipoint_golden(vb, golden, mean_func):
+    """The "VOLT + STANDARD MEAN" branch: all test points in one GeneratePrediction call (joint draw)."""
+    g = golden[f"genpred_multi_{mean_func}"]
+    vmod, vlh = vb.TrainVolModel(g["train_x"], g["vol"], train_iters=0)
+    volt, lh = vb.TrainVoltMagpieModel(g["train_x"], g["train_y"][1:], vmod, vlh, g["vol"], train_iters=0, k=g["k"],
+                                       mean_func=mean_func)
+    with torch.no_grad():
+        for n, p in volt.mean_module.named_parameters():
+            p.copy_(g["mean_params"][n])
+    from volt_b200.rollout_utils import _generate_prediction
+
+    out = _generate_prediction(volt, g["test_x"], g["pred_vol"], g["eps"].reshape(6, 5), None, 0.5, 1e-4, volt.train_x,
+                               volt.train_y, volt.log_vol_path)
+    assert relerr(out, g["samples"]) < 1e-3
+
+
+def test_rollouts_api_shapes_and_side_effects(vb, golden):
+    g = golden["rollout_ewma_none"]
+    x, px, vol = g["train_x"], g["train_y"], g["log_vol_path"].exp()
+    vmod, vlh = vb.TrainVolModel(x, vol, train_iters=2)
+    volt, lh = vb.TrainVoltMagpieModel(x, px[1:], vmod, vlh, vol, train_iters=2, k=g["k"])
+    vmod.eval()
+    torch.manual_seed(0)
+    out = vb.Rollouts(x, px, g["test_x"], volt, nsample=7)
+    assert out.shape == (7, 5) and out.device.type == "cpu" and bool(torch.isfinite(out).all())
+    assert volt.train_x.shape == (48 + 4,) and volt.train_y.shape == (7, 52) and volt.log_vol_path.shape == (7, 52)
+    # statistical sanity against the closed form (KAT-3): mean of step 0 ~ m_test + (y_last - m_last)
+    logy = px[1:].log()
+    e = O.ewma(logy, g["k"])
+    assert abs(float(out[:, 0].mean()) - float(e[-1] + logy[-1] - e[-2])) < 0.1
+
+
+@pytest.mark.parametrize("n,S,H,k", [(64, 33, 7, 5), (256, 64, 30, 25), (100, 130, 12, 100)])
+@pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma"])
+def test_rollout_vs_oracle(vb, n, S, H, k, mean_func):
+    x, vol, logy = O.synth_series(2, n, seed=31)
+    g = torch.Generator().manual_seed(n + S)
+    px = torch.cat((logy[:, :1], logy), -1).exp()
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    pred_vol = vol[:, -1:, None] * torch.exp(0.2 * torch.randn(2, S, H, generator=g))
+    eps = torch.randn(2, S, H, generator=g)
+    out, dinfo, sinfo = vb.ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind=mean_func, k=k)
+    for b in range(2):
+        want = O.rollouts(x, px[b], vol[b].log(), test_x, pred_vol[b], eps[b], k, mean_kind=mean_func)
+        assert relerr(out[b], want) < 1e-3
+        closed = O.rollout_closed_form(x.double(), px[b].double(), vol[b].log().double(), test_x.double(),
+                                       pred_vol[b].double(), eps[b].double(), k) if mean_func == "ewma" else None
+        if closed is not None:
+            assert relerr(out[b], closed) < 1e-3
+
+
+def test_rollout_philox_statistics(vb):
+    """eps=None draws in-kernel Philox normals: check first two moments of the step-0 innovation."""
+    n, S, H = 64, 4096, 3
+    x, vol, logy = O.synth_series(1, n, seed=3)
+    pred_vol = vol[:, -1:, None].expand(1, S, H).contiguous()
+    out, _, _ = vb.ops.rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=5, seed=1234)
+    out2, _, _ = vb.ops.rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=5, seed=1234)
+    assert torch.equal(out, out2)
+    e = O.ewma(logy[0], 5)
+    mu = float(e[-1] + logy[0, -1] - e[-2])
+    sd = float((0.5 * x[1]).sqrt() * vol[0, -1])
+    z = (out[0, :, 0].cpu() - mu) / sd
+    assert abs(float(z.mean())) < 0.08 and abs(float(z.std()) - 1.0) < 0.08
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_c2_properties(vb):
+    """BASELINE config 2 (1024 series x T=512): spot-check series against the oracle, finite everywhere, and the
+    gradient identity dMLL/dnoise = 1/2 (alpha.alpha - tr A^-1)/T holds on every series."""
+    B, T, k = 1024, 512, 25
+    x, vol, logy = vb.batched.synth_series(B, T)
+    xd, vd = x.cuda(), vol.cuda()
+    _, resid = vb.ops.ma_mean("ewma", logy.cuda(), k, want_resid=True)
+    raw = torch.full((B,), 1e-5).cuda()
+    out = vb.batched.mll_and_grad(xd, vd, resid, raw, check=True)
+    sc = out["scalars"]
+    assert bool(torch.isfinite(sc).all()) and int(out["info"].abs().sum()) == 0
+    ident = 0.5 * (sc[:, 5] - sc[:, 4]) / T
+    torch.testing.assert_close(sc[:, 1], ident, rtol=1e-5, atol=1e-7)
+    assert relerr((out["alpha"] * resid).sum(-1), sc[:, 3]) < 1e-3  # alpha.r == r^T A^-1 r == z.z
+    for b in (0, 511, 1023):
+        ref = O.volt_mll_and_grad(x, vol[b], resid[b].cpu(), raw[b].cpu())
+        assert relerr(out["mll"][b], ref["mll"]) < 1e-4
+        assert relerr(out["draw_noise"][b], ref["draw_noise"]) < 2e-3
+
+
+def test_full_size_c3_shape(vb):
+    """BASELINE config 3 shape (weather: T=1024, dt=1/365), reduced batch: parity on one series + identities."""
+    B, T, k = 32, 1024, 25
+    x, vol, logy = vb.batched.synth_series(B, T, dt=1.0 / 365)
+    _, resid = vb.ops.ma_mean("ewma", logy.cuda(), k, want_resid=True)
+    raw = torch.full((B,), 1e-5).cuda()
+    out = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid, raw, check=True)
+    ref = O.volt_mll_and_grad(x, vol[3], resid[3].cpu(), raw[3].cpu())
+    assert relerr(out["mll"][3], ref["mll"]) < 1e-4
+    assert relerr(out["draw_noise"][3], ref["draw_noise"]) < 2e-3

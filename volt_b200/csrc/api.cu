@@ -1,0 +1,423 @@
+// extern "C" entry points of libvolt_b200.so (declared in include/volt_b200.h).
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/volt_b200.h"
+#include "params.cuh"
+
+namespace volt {
+
+int launch_rollout_pack(const float* scalars, const float* Vt, const float* x, int B, int n, float* series, cudaStream_t st);
+int launch_gather_scalar(const float* scalars, int B, int idx, float* out, cudaStream_t st);
+
+// ---- error state
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (strstr(what, "_kernel") && !strstr(what, "cudaFunc")) ++g_launches;
+  if (e == cudaSuccess) return VOLT_OK;
+  set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return VOLT_ERR_CUDA;
+}
+
+// ---- per-device cached workspaces
+constexpr int kSlots = 12;
+struct Ws {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+static Ws g_ws[16][kSlots];
+static std::mutex g_mu;
+
+int get_workspace(size_t bytes, void** ptr, int slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || slot < 0 || slot >= kSlots) {
+    set_error("get_workspace: bad device/slot");
+    return VOLT_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  Ws& w = g_ws[dev][slot];
+  if (bytes == 0) bytes = 256;
+  if (w.bytes < bytes) {
+    if (w.ptr) {
+      cudaDeviceSynchronize();
+      cudaFree(w.ptr);
+      w.ptr = nullptr;
+      w.bytes = 0;
+    }
+    const size_t want = (bytes + (size_t)(1 << 20) - 1) / (size_t)(1 << 20) * (size_t)(1 << 20);
+    cudaError_t e = cudaMalloc(&w.ptr, want);
+    if (e != cudaSuccess) {
+      set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+      w.ptr = nullptr;
+      return VOLT_ERR_ALLOC;
+    }
+    w.bytes = want;
+  }
+  *ptr = w.ptr;
+  return VOLT_OK;
+}
+
+int sm_count() {
+  static int cached[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+static int device_check() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return VOLT_ERR_ARCH;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("volt_b200 requires an sm_100 (B200) device; found compute capability %d.x", major);
+    return VOLT_ERR_ARCH;
+  }
+  return VOLT_OK;
+}
+
+// small helper kernels that only glue outputs together
+__global__ void rollout_pack_kernel(const float* __restrict__ scalars, const float* __restrict__ Vt, const float* __restrict__ x,
+                                    int B, int n, float* __restrict__ series) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* o = series + (size_t)b * NSERIES;
+  o[0] = scalars[(size_t)b * VOLT_NSCALARS + VOLT_S_Z2Z2];
+  o[1] = scalars[(size_t)b * VOLT_NSCALARS + VOLT_S_Z1Z2];
+  o[2] = Vt[(size_t)b * n + n - 1];
+  o[3] = x[1] - x[0];
+  o[4] = scalars[(size_t)b * VOLT_NSCALARS + VOLT_S_JITTER];
+  o[5] = o[6] = o[7] = 0.f;
+}
+int launch_rollout_pack(const float* scalars, const float* Vt, const float* x, int B, int n, float* series, cudaStream_t st) {
+  rollout_pack_kernel<<<(B + 127) / 128, 128, 0, st>>>(scalars, Vt, x, B, n, series);
+  return check_cuda(cudaGetLastError(), "rollout_pack_kernel");
+}
+__global__ void gather_scalar_kernel(const float* __restrict__ scalars, int B, int idx, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = scalars[(size_t)b * VOLT_NSCALARS + idx];
+}
+int launch_gather_scalar(const float* scalars, int B, int idx, float* out, cudaStream_t st) {
+  gather_scalar_kernel<<<(B + 127) / 128, 128, 0, st>>>(scalars, B, idx, out);
+  return check_cuda(cudaGetLastError(), "gather_scalar_kernel");
+}
+
+static MllParams base_params(int B, int T, const float* resid, const float* noise, int noise_stride, float jitter, int max_tries,
+                             float* scalars, float* alpha, int* info) {
+  MllParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.T = T;
+  p.resid = resid;
+  p.diag_add = noise;
+  p.diag_stride = noise_stride;
+  p.jitter = jitter;
+  p.max_tries = max_tries;
+  p.scalars = scalars;
+  p.alpha = alpha;
+  p.info = info;
+  p.do_inverse = resid ? 1 : 0;
+  return p;
+}
+
+}  // namespace volt
+
+using namespace volt;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* volt_last_error(void) { return g_err; }
+int volt_abi_version(void) { return VOLT_ABI_VERSION; }
+int volt_device_check(void) { return device_check(); }
+long long volt_launch_count(void) { return g_launches; }
+
+int volt_cumtrapz(const float* x, int x_batched, const float* y, int B, int T, int vol_mode, int half_last, float* V, void* stream) {
+  VOLT_REQUIRE(x && y && V, "volt_cumtrapz: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 2, "volt_cumtrapz: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
+  VOLT_REQUIRE(vol_mode >= 0 && vol_mode <= 2, "volt_cumtrapz: bad vol_mode %d", vol_mode);
+  return launch_cumtrapz(x, x_batched, y, B, T, vol_mode, half_last, V, ST(stream));
+}
+
+int volt_vol_cov(const float* x, int x_batched, const float* vol, int vol_mode, int B, int T, const float* add_diag, int add_stride,
+                 float* K, void* stream) {
+  VOLT_REQUIRE(x && vol && K, "volt_vol_cov: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 2, "volt_vol_cov: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
+  void* V = nullptr;
+  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1);
+  if (s) return s;
+  s = launch_cumtrapz(x, x_batched, vol, B, T, vol_mode, 1, (float*)V, ST(stream));
+  if (s) return s;
+  return launch_vol_cov((const float*)V, add_diag, add_stride, B, T, K, ST(stream));
+}
+
+int volt_bm_cov(const float* x1, int n1, const float* x2, int n2, const float* vol, float* K, void* stream) {
+  VOLT_REQUIRE(x1 && x2 && vol && K, "volt_bm_cov: null pointer");
+  VOLT_REQUIRE(n1 >= 1 && n2 >= 1, "volt_bm_cov: empty input");
+  return launch_bm_cov(x1, n1, x2, n2, vol, K, ST(stream));
+}
+
+int volt_ewma(const float* y, int S, int T, int k, float* out, void* stream) {
+  VOLT_REQUIRE(y && out, "volt_ewma: null pointer");
+  VOLT_REQUIRE(S >= 1 && T >= 1 && k >= 1, "volt_ewma: need S,T,k >= 1 (got %d,%d,%d)", S, T, k);
+  void* w = nullptr;
+  int s = get_workspace((size_t)k * sizeof(float), &w, 2);
+  if (s) return s;
+  s = launch_ewma_weights(k, (float*)w, ST(stream));
+  if (s) return s;
+  return launch_ewma(y, S, T, k, (const float*)w, out, ST(stream));
+}
+
+int volt_ma_mean(const float* y, int S, int T, int k, int kind, float theta, const float* latent, float* out, float* e_out,
+                 float* ee_out, float* resid_out, void* stream) {
+  VOLT_REQUIRE(y && out, "volt_ma_mean: null pointer");
+  VOLT_REQUIRE(S >= 1 && T >= 1 && k >= 1, "volt_ma_mean: need S,T,k >= 1 (got %d,%d,%d)", S, T, k);
+  VOLT_REQUIRE(kind >= VOLT_MA_EWMA && kind <= VOLT_MA_MEANREVERT, "volt_ma_mean: bad kind %d", kind);
+  VOLT_REQUIRE(kind != VOLT_MA_MEANREVERT || latent, "volt_ma_mean: meanrevert needs latent");
+  void* w = nullptr;
+  int s = get_workspace((size_t)k * sizeof(float), &w, 2);
+  if (s) return s;
+  s = launch_ewma_weights(k, (float*)w, ST(stream));
+  if (s) return s;
+  return launch_ma_paths(y, S, T, k, (const float*)w, kind, theta, latent, out, e_out, ee_out, resid_out, ST(stream));
+}
+
+int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* noise,
+                      int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                      void* stream) {
+  VOLT_REQUIRE(x && vol && resid && scalars, "volt_mll_grad_vol: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
+  void* V = nullptr;
+  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1);
+  if (s) return s;
+  s = launch_cumtrapz(x, x_batched, vol, B, T, vol_mode, 1, (float*)V, ST(stream));
+  if (s) return s;
+  MllParams p = base_params(B, T, resid, noise, noise_stride, jitter, max_tries, scalars, alpha, info);
+  p.kind = KIND_VOL;
+  p.V = (const float*)V;
+  return launch_mll_batched(p, ST(stream));
+}
+
+int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise, int noise_stride,
+                     int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, void* stream) {
+  VOLT_REQUIRE(x && scale && resid && scalars, "volt_mll_grad_bm: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 1, "volt_mll_grad_bm: need B,T >= 1");
+  MllParams p = base_params(B, T, resid, noise, noise_stride, jitter, max_tries, scalars, alpha, info);
+  p.kind = KIND_BM;
+  p.x = x;
+  p.scale = scale;
+  p.scale_stride = scale_stride;
+  return launch_mll_batched(p, ST(stream));
+}
+
+int volt_mll_grad_dense(const float* K, long long k_bstride, int ld, const float* resid, const float* noise, int noise_stride, int B,
+                        int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, void* stream) {
+  VOLT_REQUIRE(K && resid && scalars, "volt_mll_grad_dense: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 1 && ld >= T, "volt_mll_grad_dense: bad shape");
+  MllParams p = base_params(B, T, resid, noise, noise_stride, jitter, max_tries, scalars, alpha, info);
+  p.kind = KIND_DENSE;
+  p.dense = K;
+  p.dense_bstride = k_bstride;
+  p.ldd = ld;
+  return launch_mll_batched(p, ST(stream));
+}
+
+int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid, const float* noise, int noise_stride, int B, int T,
+                           float jitter, int max_tries, float* scalars, float* alpha, int* info) {
+  VOLT_REQUIRE(x && vol && resid && noise && scalars, "volt_mll_grad_vol_host: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol_host: need B >= 1 and T >= 2");
+  const size_t bt = (size_t)B * T;
+  const size_t n_noise = noise_stride ? (size_t)B : 1;
+  // one staging buffer: x | vol | resid | noise | scalars | alpha | info
+  const size_t floats = (size_t)T + bt + bt + n_noise + (size_t)B * VOLT_NSCALARS + bt + (size_t)B;
+  void* ws = nullptr;
+  int s = get_workspace(floats * sizeof(float), &ws, 3);
+  if (s) return s;
+  float* d_x = (float*)ws;
+  float* d_vol = d_x + T;
+  float* d_res = d_vol + bt;
+  float* d_noise = d_res + bt;
+  float* d_scal = d_noise + n_noise;
+  float* d_alpha = d_scal + (size_t)B * VOLT_NSCALARS;
+  int* d_info = (int*)(d_alpha + bt);
+  cudaStream_t st = 0;
+  VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+  VOLT_CUDA(cudaMemcpyAsync(d_vol, vol, bt * 4, cudaMemcpyHostToDevice, st));
+  VOLT_CUDA(cudaMemcpyAsync(d_res, resid, bt * 4, cudaMemcpyHostToDevice, st));
+  VOLT_CUDA(cudaMemcpyAsync(d_noise, noise, n_noise * 4, cudaMemcpyHostToDevice, st));
+  s = volt_mll_grad_vol(d_x, 0, d_vol, VOLT_VOL_SIGMA, d_res, d_noise, noise_stride, B, T, jitter, max_tries, d_scal,
+                        alpha ? d_alpha : nullptr, d_info, st);
+  if (s) return s;
+  VOLT_CUDA(cudaMemcpyAsync(scalars, d_scal, (size_t)B * VOLT_NSCALARS * 4, cudaMemcpyDeviceToHost, st));
+  if (alpha) VOLT_CUDA(cudaMemcpyAsync(alpha, d_alpha, bt * 4, cudaMemcpyDeviceToHost, st));
+  if (info) VOLT_CUDA(cudaMemcpyAsync(info, d_info, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  VOLT_CUDA(cudaStreamSynchronize(st));
+  return VOLT_OK;
+}
+
+int volt_potrf(const float* A, long long a_bstride, int lda, const float* add_diag, int add_stride, int B, int T, float jitter,
+               int max_tries, float* L, long long l_bstride, int ldl, float* jitter_used, int* info, void* stream) {
+  VOLT_REQUIRE(A && L, "volt_potrf: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 1 && lda >= T && ldl >= T, "volt_potrf: bad shape");
+  void* sc = nullptr;
+  int s = get_workspace((size_t)B * VOLT_NSCALARS * sizeof(float), &sc, 4);
+  if (s) return s;
+  MllParams p = base_params(B, T, nullptr, add_diag, add_stride, jitter, max_tries, (float*)sc, nullptr, info);
+  p.kind = KIND_DENSE;
+  p.dense = A;
+  p.dense_bstride = a_bstride;
+  p.ldd = lda;
+  p.L_out = L;
+  p.L_bstride = l_bstride;
+  p.ldl = ldl;
+  s = launch_mll_batched(p, ST(stream));
+  if (s) return s;
+  if (jitter_used) return launch_gather_scalar((const float*)sc, B, VOLT_S_JITTER, jitter_used, ST(stream));
+  return VOLT_OK;
+}
+
+int volt_potrs(const float* L, long long l_bstride, int ldl, int B, int T, float* rhs, long long r_bstride, int nrhs,
+               int forward_only, void* stream) {
+  VOLT_REQUIRE(L && rhs, "volt_potrs: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 1 && nrhs >= 1 && ldl >= T, "volt_potrs: bad shape");
+  return launch_chol_solve(L, l_bstride, ldl, B, T, rhs, r_bstride, nrhs, forward_only ? 1 : 0, ST(stream));
+}
+
+int volt_bmgp_posterior(const float* x, const float* y, int B, int T, const float* xs, int H, const float* vol, int vol_stride,
+                        const float* noise, int noise_stride, float* mean, float* cov, int* info, void* stream) {
+  VOLT_REQUIRE(x && y && xs && vol && noise && mean && cov, "volt_bmgp_posterior: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 1 && H >= 1, "volt_bmgp_posterior: bad shape");
+  const size_t wfl = (size_t)B * T * (H + 1) + (size_t)B * H * H + (size_t)B * H + (size_t)B * VOLT_NSCALARS;
+  void* ws = nullptr;
+  int s = get_workspace(wfl * sizeof(float), &ws, 5);
+  if (s) return s;
+  float* W0 = (float*)ws;
+  float* Kss = W0 + (size_t)B * T * (H + 1);
+  float* mean_s = Kss + (size_t)B * H * H;
+  float* scal = mean_s + (size_t)B * H;
+  void* Lw = nullptr;
+  s = get_workspace((size_t)B * T * T * sizeof(float), &Lw, 6);
+  if (s) return s;
+  s = launch_bm_posterior_pack(x, B, T, xs, H, y, vol, vol_stride, W0, Kss, mean_s, nullptr, ST(stream));
+  if (s) return s;
+  MllParams p = base_params(B, T, nullptr, noise, noise_stride, 1e-6f, 3, scal, nullptr, info);
+  p.kind = KIND_BM;
+  p.x = x;
+  p.scale = vol;
+  p.scale_stride = vol_stride;
+  p.L_out = (float*)Lw;
+  p.L_bstride = (long long)T * T;
+  p.ldl = T;
+  s = launch_mll_batched(p, ST(stream));
+  if (s) return s;
+  s = launch_chol_solve((const float*)Lw, (long long)T * T, T, B, T, W0, (long long)T * (H + 1), H + 1, 1, ST(stream));
+  if (s) return s;
+  return launch_posterior(W0, B, T, H, Kss, mean_s, mean, cov, ST(stream));
+}
+
+int volt_mvn_sample(const float* mean, const float* cov, const float* eps, int B, int H, int S, float jitter, int exp_out,
+                    float* samples, int* info, void* stream) {
+  VOLT_REQUIRE(mean && cov && eps && samples, "volt_mvn_sample: null pointer");
+  VOLT_REQUIRE(B >= 1 && H >= 1 && S >= 1, "volt_mvn_sample: bad shape");
+  void* Lc = nullptr;
+  int s = get_workspace((size_t)B * H * H * sizeof(float), &Lc, 7);
+  if (s) return s;
+  s = volt_potrf(cov, (long long)H * H, H, nullptr, 0, B, H, jitter, 3, (float*)Lc, (long long)H * H, H, nullptr, info, stream);
+  if (s) return s;
+  return launch_mvn_sample(mean, (const float*)Lc, eps, B, H, S, exp_out, samples, ST(stream));
+}
+
+int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mode, const float* pred_vol, const float* eps, int B,
+                 int n, int S, int H, int mean_kind, int k, float mr_theta, const float* mr_latent, const float* resid_given,
+                 const float* mean_test, int use_theta, float theta, const float* latent, int joint, float jitter,
+                 unsigned long long seed, float* samples, int* draw_info, int* series_info, void* stream) {
+  VOLT_REQUIRE(x && logy && vol && pred_vol && samples, "volt_rollout: null pointer");
+  VOLT_REQUIRE(B >= 1 && n >= 2 && S >= 1 && H >= 1, "volt_rollout: bad shape (B=%d n=%d S=%d H=%d)", B, n, S, H);
+  VOLT_REQUIRE(mean_kind >= VOLT_MA_EWMA && mean_kind <= VOLT_MA_GIVEN, "volt_rollout: bad mean_kind %d", mean_kind);
+  const bool ma = mean_kind != VOLT_MA_GIVEN;
+  VOLT_REQUIRE(!ma || k >= 1, "volt_rollout: moving-average means need k >= 1");
+  VOLT_REQUIRE(ma || (resid_given && (mean_test || !joint)), "volt_rollout: VOLT_MA_GIVEN needs resid_given (and mean_test)");
+  VOLT_REQUIRE(!(joint && ma && H > 1), "volt_rollout: the moving-average means support one test point per call (EWMA.py:48-54)");
+  VOLT_REQUIRE(mean_kind != VOLT_MA_MEANREVERT || mr_latent, "volt_rollout: meanrevert needs mr_latent");
+  VOLT_REQUIRE(!use_theta || latent, "volt_rollout: use_theta needs latent");
+  cudaStream_t st = ST(stream);
+  // workspace: Vt (B,n) | path,e,ee (B,n+1)x3 | resid (B,n) | scalars (B,16) | series (B,4) | w (k) | sinfo (B)
+  const size_t bn = (size_t)B * n, bn1 = (size_t)B * (n + 1);
+  const size_t fl = bn + 3 * bn1 + bn + (size_t)B * VOLT_NSCALARS + (size_t)B * NSERIES + (size_t)(k > 0 ? k : 1) + (size_t)B;
+  void* ws = nullptr;
+  int s = get_workspace(fl * sizeof(float), &ws, 8);
+  if (s) return s;
+  float* Vt = (float*)ws;
+  float* path = Vt + bn;
+  float* e_tr = path + bn1;
+  float* ee_tr = e_tr + bn1;
+  float* resid = ee_tr + bn1;
+  float* scal = resid + bn;
+  float* series = scal + (size_t)B * VOLT_NSCALARS;
+  float* w = series + (size_t)B * NSERIES;
+  int* sinfo = (int*)(w + (k > 0 ? k : 1));
+  s = launch_cumtrapz(x, 0, vol, B, n, vol_mode, 0, Vt, st);
+  if (s) return s;
+  const float* r1 = resid_given;
+  if (ma) {
+    s = launch_ewma_weights(k, w, st);
+    if (s) return s;
+    s = launch_ma_paths(logy, B, n, k, w, mean_kind, mr_theta, mr_latent, path, e_tr, ee_tr, resid, st);
+    if (s) return s;
+    r1 = resid;
+  }
+  MllParams p = base_params(B, n, r1, nullptr, 0, jitter, 3, scal, nullptr, series_info ? series_info : sinfo);
+  p.kind = KIND_VOL;
+  p.V = Vt;
+  p.resid2 = Vt;
+  p.do_inverse = 0;
+  s = launch_mll_batched(p, st);
+  if (s) return s;
+  s = launch_rollout_pack(scal, Vt, x, B, n, series, st);
+  if (s) return s;
+  RolloutParams q;
+  memset(&q, 0, sizeof(q));
+  q.B = B; q.n = n; q.S = S; q.H = H; q.k = ma ? k : 0; q.mean_kind = mean_kind; q.joint = joint;
+  q.w = ma ? w : nullptr;
+  q.ytrain = logy;
+  q.e_train = ma ? e_tr : nullptr;
+  q.ee_train = ma ? ee_tr : nullptr;
+  q.mean_test = mean_test;
+  q.series = series;
+  q.series_info = series_info ? series_info : sinfo;
+  q.pred_vol = pred_vol;
+  q.eps = eps;
+  q.latent = latent;
+  q.theta = theta;
+  q.use_theta = use_theta;
+  q.mr_latent = mr_latent;
+  q.mr_theta = mr_theta;
+  q.jitter = jitter;
+  q.seed = seed;
+  q.samples = samples;
+  q.info = draw_info;
+  return launch_rollout(q, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Parameter blocks and launcher prototypes shared by the kernel translation units and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace volt {
+
+enum { KIND_DENSE = 0, KIND_VOL = 1, KIND_BM = 2 };
+enum { MA_EWMA = 0, MA_DEWMA = 1, MA_TEWMA = 2, MA_MEANREVERT = 3, MA_GIVEN = 4 };
+constexpr int NSCALARS = 16;
+constexpr int NSERIES = 8;  // floats per series handed to the rollout: u.u, u.z1, V[n-1], dx, jitter, 0, 0, 0
+
+struct MllParams {
+  int kind, B, T, Tp, nb;
+  const float* dense; long long dense_bstride; int ldd;
+  const float* V;                       // (B,T) cumtrapz prefix (KIND_VOL)
+  const float* x;                       // (T) grid (KIND_BM)
+  const float* scale; int scale_stride; // BM vol (per series or shared)
+  const float* diag_add; int diag_stride;
+  const float* resid;                   // (B,T) or null
+  const float* resid2;                  // (B,T) or null: second right-hand side (forward substitution only)
+  float* z_out;                         // (B,2,T) or null: z1 = L^-1 resid, z2 = L^-1 resid2
+  float* scalars;                       // (B,16): see VOLT_S_* in include/volt_b200.h
+  float* alpha;                         // (B,T) or null
+  int* info;                            // (B) or null
+  float* L_out; long long L_bstride; int ldl;
+  int do_inverse;
+  float jitter; int max_tries;
+  float* scratch;                       // gridDim.x * Tp * Tp
+  float* dinv;                          // gridDim.x * nb * 64 * 64
+};
+
+struct RolloutParams {
+  int B, n, S, H, k, mean_kind, joint;   // joint = 1: one-shot multi-point draw (no feedback of samples)
+  const float* w;          // (k) EWMA weights
+  const float* ytrain;     // (B,n) log prices
+  const float* e_train;    // (B,n+1) EWMA path of ytrain       (MA kinds)
+  const float* ee_train;   // (B,n+1) EWMA(e)[:-1]              (DEWMA/TEWMA)
+  const float* mean_test;  // (B,H) parametric test means       (MA_GIVEN)
+  const float* series;     // (B,NSERIES)
+  const int* series_info;  // (B) potrf info of the shared block
+  const float* pred_vol;   // (B,S,H)
+  const float* eps;        // (B,S,H) or null
+  const float* latent;     // (B) rollout-level mean reversion target (theta) or null
+  float theta; int use_theta;
+  const float* mr_latent;  // (B) MeanRevertingEMAMean.latent_mean
+  float mr_theta;
+  float jitter;            // psd_safe_cholesky jitter for pred_cov (1e-4 in rollout_utils, 1e-6 default)
+  unsigned long long seed;
+  float* samples;          // (B,S,H)
+  int* info;               // (B,S) bit0: per-draw pivot failure, bit1: pred_cov needed jitter, bit2: not PSD after jitter
+  int Hp;                  // padded tile row length (odd)
+};
+
+int launch_mll_batched(MllParams p, cudaStream_t st);
+int launch_rollout(RolloutParams p, cudaStream_t st);
+int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kind, float theta, const float* latent, float* out,
+                    float* e_out, float* ee_out, float* resid_out, cudaStream_t st);
+int launch_cumtrapz(const float* x, int x_batched, const float* vol, int B, int T, int mode, int half_last, float* V,
+                    cudaStream_t st);
+int launch_vol_cov(const float* V, const float* add_diag, int add_stride, int B, int T, float* K, cudaStream_t st);
+int launch_bm_cov(const float* x1, int n1, const float* x2, int n2, const float* vol, float* K, cudaStream_t st);
+int launch_ewma_weights(int k, float* w_dev, cudaStream_t st);
+int launch_ewma(const float* y, int S, int T, int k, const float* w_dev, float* out, cudaStream_t st);
+int launch_chol_solve(const float* L, long long l_bstride, int ldl, int B, int T, float* rhs, long long r_bstride, int nrhs,
+                      int mode, cudaStream_t st);
+int launch_posterior(const float* W, int B, int T, int H, const float* Kss, const float* mean_s, float* mean, float* cov,
+                     cudaStream_t st);
+int launch_bm_posterior_pack(const float* x, int B, int T, const float* xs, int H, const float* y, const float* vol,
+                             int vol_stride, float* W0, float* Kss, float* mean_s, float* resid, cudaStream_t st);
+int launch_mvn_sample(const float* mean, const float* Lc, const float* eps, int B, int H, int S, int exp_out, float* samples,
+                      cudaStream_t st);
+
+}  // namespace volt

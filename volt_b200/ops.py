@@ -1,0 +1,360 @@
+"""Tensor-level wrappers of the C ABI (device pointers come from torch tensors; torch is only the allocator/stream
+provider here) and the autograd bridge for the exact marginal log-likelihood.
+
+Every function accepts CPU or CUDA float tensors: CPU inputs are moved to the current CUDA device and results are
+returned on the input's device, which is what lets the reference's CPU-tensor call sites run unchanged.
+"""
+import torch
+
+from . import _lib
+from ._lib import (MA_DEWMA, MA_EWMA, MA_GIVEN, MA_MEANREVERT, MA_TEWMA, S_ALAL, S_ALR, S_DNOISE, S_JITTER, S_MLL, S_TRINV,
+                   VOL_LOGSIGMA, VOL_RAW, VOL_SIGMA, VOLT_NSCALARS)
+
+MA_KINDS = {"ewma": MA_EWMA, "dewma": MA_DEWMA, "tewma": MA_TEWMA, "meanrevert": MA_MEANREVERT, "given": MA_GIVEN}
+
+
+class NotPSDError(RuntimeError):
+    """Raised when a matrix is not positive definite after the psd_safe_cholesky jitter retries
+    ([GPyTorch] gpytorch.utils.errors.NotPSDError)."""
+
+
+class NumericalWarning(RuntimeWarning):
+    """[GPyTorch] gpytorch.utils.warnings.NumericalWarning."""
+
+
+def _dev():
+    _lib.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f32(t, dev):
+    """contiguous float32 tensor on `dev` (no copy when it already is)."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _back(t, like):
+    return t if (torch.is_tensor(like) and like.is_cuda) else t.cpu()
+
+
+def _empty(shape, dev, dtype=torch.float32):
+    return torch.empty(shape, device=dev, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------ covariance
+def cumtrapz(y, x, vol_mode=VOL_RAW, half_last=True):
+    """CumTrapz(y, x) -- voltron/kernels/VolKernel.py:4-10."""
+    dev = _dev()
+    lead = y.shape[:-1]
+    T = y.shape[-1]
+    yd = _f32(y, dev).reshape(-1, T)
+    xd = _f32(x, dev)
+    x_batched = int(xd.ndim > 1)
+    if x_batched:
+        xd = xd.expand(*lead, T).reshape(-1, T).contiguous()
+    out = _empty(yd.shape, dev)
+    _lib.check(_lib.load().volt_cumtrapz(_ptr(xd), x_batched, _ptr(yd), yd.shape[0], T, vol_mode, int(half_last), _ptr(out),
+                                         _stream()), "volt_cumtrapz")
+    return _back(out.reshape(*lead, T), y)
+
+
+def vol_cov(x, vol, add_diag=None, vol_mode=VOL_SIGMA):
+    """VolatilityKernel.forward: K[..., i, j] = V[..., min(i, j)] -- voltron/kernels/VolKernel.py:18-41."""
+    dev = _dev()
+    lead = vol.shape[:-1]
+    T = vol.shape[-1]
+    vd = _f32(vol, dev).reshape(-1, T)
+    xd = _f32(x, dev)
+    x_batched = int(xd.ndim > 1)
+    if x_batched:
+        xd = xd.expand(*lead, T).reshape(-1, T).contiguous()
+    B = vd.shape[0]
+    ad, astride = None, 0
+    if add_diag is not None:
+        ad = _f32(add_diag, dev).reshape(-1)
+        astride = 0 if ad.numel() == 1 else 1
+    K = _empty((B, T, T), dev)
+    _lib.check(_lib.load().volt_vol_cov(_ptr(xd), x_batched, _ptr(vd), vol_mode, B, T, _ptr(ad), astride, _ptr(K), _stream()),
+               "volt_vol_cov")
+    return _back(K.reshape(*lead, T, T), vol)
+
+
+def bm_cov(x1, x2, vol):
+    """BMKernel.forward: vol * min(x1_i, x2_j) -- voltron/kernels/BMKernel.py:38-51."""
+    dev = _dev()
+    a, b, v = _f32(x1, dev).reshape(-1), _f32(x2, dev).reshape(-1), _f32(vol, dev).reshape(-1)
+    K = _empty((a.numel(), b.numel()), dev)
+    _lib.check(_lib.load().volt_bm_cov(_ptr(a), a.numel(), _ptr(b), b.numel(), _ptr(v), _ptr(K), _stream()), "volt_bm_cov")
+    return _back(K, x1)
+
+
+# ------------------------------------------------------------------------------------------------ moving averages
+def ewma(y, k):
+    """EWMA(y, k) -- voltron/means/EWMA.py:20-37.  (..., T) -> (..., T+1)."""
+    dev = _dev()
+    lead, T = y.shape[:-1], y.shape[-1]
+    yd = _f32(y, dev).reshape(-1, T)
+    out = _empty((yd.shape[0], T + 1), dev)
+    _lib.check(_lib.load().volt_ewma(_ptr(yd), yd.shape[0], T, int(k), _ptr(out), _stream()), "volt_ewma")
+    return _back(out.reshape(*lead, T + 1), y)
+
+
+def ma_mean(kind, y, k, theta=0.5, latent=None, want_resid=False):
+    """Full-length (T+1) path of EWMAMean / DEWMAMean / TEWMAMean / MeanRevertingEMAMean -- voltron/means/EWMA.py:39-135."""
+    dev = _dev()
+    lead, T = y.shape[:-1], y.shape[-1]
+    yd = _f32(y, dev).reshape(-1, T)
+    S = yd.shape[0]
+    kid = MA_KINDS[kind.lower()]
+    lat = None
+    if kid == MA_MEANREVERT:
+        lat = _f32(latent, dev).reshape(-1)
+        if lat.numel() == 1:
+            lat = lat.expand(S).contiguous()
+    out = _empty((S, T + 1), dev)
+    resid = _empty((S, T), dev) if want_resid else None
+    _lib.check(_lib.load().volt_ma_mean(_ptr(yd), S, T, int(k), kid, float(theta), _ptr(lat), _ptr(out), None, None, _ptr(resid),
+                                        _stream()), "volt_ma_mean")
+    out = _back(out.reshape(*lead, T + 1), y)
+    if want_resid:
+        return out, _back(resid.reshape(*lead, T), y)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ exact MLL
+def _check_info(info, jitter_used, what):
+    """psd_safe_cholesky reporting: warn when jitter was needed, raise when the retries were exhausted."""
+    import warnings
+
+    bad = info.nonzero()
+    if bad.numel():
+        raise NotPSDError(f"{what}: matrix not positive definite after repeatedly adding jitter "
+                          f"(first failing series {int(bad[0])}, leading minor {int(info[bad[0]])})")
+    if jitter_used is not None and bool((jitter_used > 0).any()):
+        warnings.warn(f"A not p.d., added jitter of {float(jitter_used.max()):.1e} to the diagonal", NumericalWarning)
+
+
+def mll_grad(kind, x, gen, resid, noise, jitter=1e-6, max_tries=3, vol_mode=VOL_SIGMA, check=True, want_alpha=True):
+    """One exact MLL + gradient evaluation per series (fused build + potrf + solves + trtri on the GPU).
+
+    kind: "vol" (gen = vol path (B,T)), "bm" (gen = BM scale (B,) or scalar), "dense" (gen = K (B,T,T)).
+    resid (B,T) = y - mean, noise (B,) or scalar.  Returns dict of CUDA tensors: scalars (B,16), alpha (B,T), info (B).
+    Call sites replaced: voltron/train_utils.py:89-90,136-137,249-250."""
+    dev = _dev()
+    lib = _lib.load()
+    r = _f32(resid, dev)
+    T = r.shape[-1]
+    r = r.reshape(-1, T)
+    B = r.shape[0]
+    nz = _f32(noise, dev).reshape(-1)
+    nstride = 0 if nz.numel() == 1 else 1
+    if nstride and nz.numel() != B:
+        raise ValueError("noise must be a scalar or have one entry per series")
+    scal = _empty((B, VOLT_NSCALARS), dev)
+    alpha = _empty((B, T), dev) if want_alpha else None
+    info = _empty((B,), dev, torch.int32)
+    st = _stream()
+    if kind == "vol":
+        g = _f32(gen, dev).reshape(-1, T)
+        if g.shape[0] != B:
+            g = g.expand(B, T).contiguous()
+        xd = _f32(x, dev)
+        xb = int(xd.ndim > 1)
+        if xb:
+            xd = xd.reshape(-1, T)
+        _lib.check(lib.volt_mll_grad_vol(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(nz), nstride, B, T, float(jitter),
+                                         int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), st), "volt_mll_grad_vol")
+    elif kind == "bm":
+        xd = _f32(x, dev).reshape(-1)
+        sc = _f32(gen, dev).reshape(-1)
+        sstride = 0 if sc.numel() == 1 else 1
+        _lib.check(lib.volt_mll_grad_bm(_ptr(xd), _ptr(sc), sstride, _ptr(r), _ptr(nz), nstride, B, T, float(jitter),
+                                        int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), st), "volt_mll_grad_bm")
+    elif kind == "dense":
+        Kd = _f32(gen, dev).reshape(-1, T, T)
+        kb = T * T if Kd.shape[0] == B else 0
+        _lib.check(lib.volt_mll_grad_dense(_ptr(Kd), kb, T, _ptr(r), _ptr(nz), nstride, B, T, float(jitter), int(max_tries),
+                                           _ptr(scal), _ptr(alpha), _ptr(info), st), "volt_mll_grad_dense")
+    else:
+        raise ValueError(kind)
+    if check:
+        _check_info(info, scal[:, S_JITTER], "exact MLL")
+    return dict(scalars=scal, alpha=alpha, info=info)
+
+
+class _ExactMLL(torch.autograd.Function):
+    """-> per-series MLL (GPyTorch normalisation, / T).  Analytic backward:
+    dMLL/dresid = -alpha/T, dMLL/dnoise = 1/2 (alpha.alpha - tr A^-1)/T, and for the BM kernel
+    dMLL/dscale = 1/2 [(alpha.r - noise alpha.alpha) - (T - noise tr A^-1)] / (scale T)."""
+
+    @staticmethod
+    def forward(ctx, kind, x, gen, resid, noise, jitter, vol_mode):
+        out = mll_grad(kind, x, gen, resid, noise, jitter=jitter, vol_mode=vol_mode)
+        sc = out["scalars"]
+        ctx.kind, ctx.T, ctx.in_dev = kind, resid.shape[-1], resid.device
+        ctx.rshape, ctx.nshape = tuple(resid.shape), tuple(noise.shape)
+        ctx.gshape = tuple(gen.shape) if kind == "bm" else None
+        nz = noise.detach().to(sc.device, torch.float32).reshape(-1)
+        g = gen.detach().to(sc.device, torch.float32).reshape(-1) if kind == "bm" else sc.new_zeros(1)
+        ctx.save_for_backward(sc, out["alpha"], nz, g)
+        return sc[:, S_MLL].clone().to(resid.device).reshape(resid.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, grad):
+        sc, alpha, noise, scale = ctx.saved_tensors
+        T = ctx.T
+        gd = grad.to(sc.device, torch.float32).reshape(-1)
+
+        def fold(v, shape):
+            n = 1
+            for d in shape:
+                n *= d
+            v = v.sum() if n == 1 else v
+            return v.reshape(shape).to(ctx.in_dev)
+
+        d_resid = ((-alpha / T) * gd[:, None]).reshape(ctx.rshape).to(ctx.in_dev)
+        d_noise = fold(sc[:, S_DNOISE] * gd, ctx.nshape)
+        d_gen = None
+        if ctx.kind == "bm":
+            ds = 0.5 * ((sc[:, S_ALR] - noise * sc[:, S_ALAL]) - (T - noise * sc[:, S_TRINV])) / (scale * T)
+            d_gen = fold(ds * gd, ctx.gshape)
+        return None, None, d_gen, d_resid, d_noise, None, None
+
+
+def exact_mll(kind, x, gen, resid, noise, jitter=1e-6, vol_mode=VOL_SIGMA):
+    """Differentiable exact marginal log-likelihood per series (already divided by T).  Gradients flow to resid (mean
+    parameters), noise (raw_noise) and, for kind == "bm", gen = the BM scale (raw_vol).  A vol path / dense K is a
+    constant, as in the reference where train_cov is detached (VoltMagpie.py:46)."""
+    if kind != "bm" and torch.is_tensor(gen) and gen.requires_grad:
+        raise NotImplementedError("gradients w.r.t. the covariance generator are only provided for the BM scale")
+    return _ExactMLL.apply(kind, x, gen, resid, noise, jitter, vol_mode)
+
+
+# ------------------------------------------------------------------------------------------------ Cholesky utilities
+def potrf(A, jitter=None, max_tries=3, check=True):
+    """psd_safe_cholesky(A, jitter) -- [GPyTorch]; call sites voltron/rollout_utils.py:35,46, VoltMagpie.py:87,92.
+    Returns (L, info, jitter_used) with L lower-triangular (upper part zeroed), batched over leading dims."""
+    dev = _dev()
+    T = A.shape[-1]
+    lead = A.shape[:-2]
+    Ad = _f32(A, dev).reshape(-1, T, T)
+    B = Ad.shape[0]
+    L = _empty((B, T, T), dev)
+    info = _empty((B,), dev, torch.int32)
+    ju = _empty((B,), dev)
+    if jitter is None:
+        jitter = 1e-6
+    _lib.check(_lib.load().volt_potrf(_ptr(Ad), T * T, T, None, 0, B, T, float(jitter), int(max_tries), _ptr(L), T * T, T,
+                                      _ptr(ju), _ptr(info), _stream()), "volt_potrf")
+    if check:
+        _check_info(info, ju, "psd_safe_cholesky")
+    return _back(L.reshape(*lead, T, T), A), info, ju
+
+
+def potrs(L, rhs, forward_only=False):
+    """torch.cholesky_solve(rhs, L) -- voltron/rollout_utils.py:36,44.  rhs (..., T, nrhs)."""
+    dev = _dev()
+    T = L.shape[-1]
+    Ld = _f32(L, dev).reshape(-1, T, T)
+    B = Ld.shape[0]
+    R = _f32(rhs, dev).reshape(-1, T, rhs.shape[-1]).clone()
+    if R.shape[0] != B:
+        R = R.expand(B, T, rhs.shape[-1]).contiguous()
+    nrhs = R.shape[-1]
+    _lib.check(_lib.load().volt_potrs(_ptr(Ld), T * T, T, B, T, _ptr(R), T * nrhs, nrhs, int(forward_only), _stream()),
+               "volt_potrs")
+    return _back(R.reshape(*L.shape[:-2], T, nrhs), rhs)
+
+
+def bmgp_posterior(x, y, xs, vol, noise):
+    """BMGP eval-mode posterior at test points xs -- voltron/models/BMGP.py:18-28, rollout_utils.py:66.
+    x (T), y (T) or (B,T), xs (H); vol / noise scalar or (B,).  Returns mean (B,H), cov (B,H,H) on the GPU."""
+    dev = _dev()
+    xd, xsd = _f32(x, dev).reshape(-1), _f32(xs, dev).reshape(-1)
+    T, H = xd.numel(), xsd.numel()
+    yd = _f32(y, dev).reshape(-1, T)
+    B = yd.shape[0]
+    v, nz = _f32(vol, dev).reshape(-1), _f32(noise, dev).reshape(-1)
+    mean, cov = _empty((B, H), dev), _empty((B, H, H), dev)
+    info = _empty((B,), dev, torch.int32)
+    _lib.check(_lib.load().volt_bmgp_posterior(_ptr(xd), _ptr(yd), B, T, _ptr(xsd), H, _ptr(v), 0 if v.numel() == 1 else 1,
+                                               _ptr(nz), 0 if nz.numel() == 1 else 1, _ptr(mean), _ptr(cov), _ptr(info),
+                                               _stream()), "volt_bmgp_posterior")
+    _check_info(info, None, "BMGP posterior")
+    return mean, cov
+
+
+def mvn_sample(mean, cov, eps, jitter=1e-6, exp_out=False):
+    """MultivariateNormal.sample: mean + psd_safe_cholesky(cov) eps.  mean (B,H), cov (B,H,H), eps (B,H,S) -> (B,S,H)."""
+    dev = _dev()
+    m, c, e = _f32(mean, dev), _f32(cov, dev), _f32(eps, dev)
+    H = m.shape[-1]
+    m, c = m.reshape(-1, H), c.reshape(-1, H, H)
+    B = m.shape[0]
+    e = e.reshape(B, H, -1)
+    S = e.shape[-1]
+    out = _empty((B, S, H), dev)
+    info = _empty((B,), dev, torch.int32)
+    _lib.check(_lib.load().volt_mvn_sample(_ptr(m), _ptr(c), _ptr(e), B, H, S, float(jitter), int(exp_out), _ptr(out), _ptr(info),
+                                           _stream()), "volt_mvn_sample")
+    _check_info(info, None, "MultivariateNormal.sample")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ rollout
+def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0.5, mr_latent=None, resid_given=None,
+            mean_test=None, theta=None, latent=None, joint=False, jitter=1e-4, seed=0, vol_mode=VOL_SIGMA, check=True):
+    """GeneratePrediction / Rollouts on the GPU -- voltron/rollout_utils.py:6-93.
+
+    x (n,), logy (B,n) or (n,), vol (B,n) or (n,), pred_vol (B,S,H) or (S,H), eps like pred_vol or None (Philox).
+    Returns samples (B,S,H) (CUDA), draw_info (B,S), series_info (B)."""
+    dev = _dev()
+    xd = _f32(x, dev).reshape(-1)
+    n = xd.numel()
+    ly = _f32(logy, dev).reshape(-1, n)
+    B = ly.shape[0]
+    vd = _f32(vol, dev).reshape(-1, n)
+    if vd.shape[0] != B:
+        vd = vd.expand(B, n).contiguous()
+    pv = _f32(pred_vol, dev)
+    H = pv.shape[-1]
+    pv = pv.reshape(B, -1, H)
+    S = pv.shape[1]
+    ep = None if eps is None else _f32(eps, dev).reshape(B, S, H)
+    kid = MA_KINDS[mean_kind.lower()]
+
+    def per_series(t):
+        if t is None:
+            return None
+        t = _f32(t, dev).reshape(-1)
+        return t.expand(B).contiguous() if t.numel() == 1 else t
+
+    mrl = per_series(mr_latent)
+    lat = per_series(latent)
+    rg = None if resid_given is None else _f32(resid_given, dev).reshape(B, n)
+    mt = None if mean_test is None else _f32(mean_test, dev).reshape(-1, H)
+    if mt is not None and mt.shape[0] != B:
+        mt = mt.expand(B, H).contiguous()
+    out = _empty((B, S, H), dev)
+    dinfo = _empty((B, S), dev, torch.int32)
+    sinfo = _empty((B,), dev, torch.int32)
+    use_theta = int(theta is not None and lat is not None)
+    _lib.check(_lib.load().volt_rollout(_ptr(xd), _ptr(ly), _ptr(vd), vol_mode, _ptr(pv), _ptr(ep), B, n, S, H, kid, int(k),
+                                        float(mr_theta), _ptr(mrl), _ptr(rg), _ptr(mt), use_theta,
+                                        float(theta if theta is not None else 0.0), _ptr(lat), int(joint), float(jitter),
+                                        int(seed), _ptr(out), _ptr(dinfo), _ptr(sinfo), _stream()), "volt_rollout")
+    if check:
+        if bool(sinfo.any()):
+            raise NotPSDError("rollout: training covariance not positive definite after jitter retries")
+        if bool((dinfo & 5).any()):
+            raise NotPSDError("rollout: a conditional covariance was not positive definite after jitter retries")
+    return out, dinfo, sinfo
