@@ -65,6 +65,10 @@ int volt_abi_version(void);
 int volt_device_check(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches counter) */
 long long volt_launch_count(void);
+/* Select the batched Cholesky/MLL kernel: 1 = tcgen05 3xTF32 tensor-core products (default), 0 = fp32 CUDA-core
+ * products (kept for A/B measurement; both are CUDA paths).  Also settable with VOLT_MLL_IMPL=tc|simt.  Returns the
+ * previous setting (-1 if never set). */
+int volt_set_mll_impl(int impl);
 
 /* CumTrapz(y, x)  -- voltron/kernels/VolKernel.py:4-10.
  * x (T) or (B,T) if x_batched; y (B,T) encoded per `vol_mode`; half_last=1 reproduces the reference weights

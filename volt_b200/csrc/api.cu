@@ -1,5 +1,6 @@
 // extern "C" entry points of libvolt_b200.so (declared in include/volt_b200.h).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -122,6 +123,16 @@ int launch_gather_scalar(const float* scalars, int B, int idx, float* out, cudaS
   return check_cuda(cudaGetLastError(), "gather_scalar_kernel");
 }
 
+// implementation switch for the batched MLL kernel: 1 = tcgen05 (default), 0 = SIMT fp32 (kept for A/B measurement)
+static int g_mll_impl = -1;
+int launch_mll_batched(MllParams p, cudaStream_t st) {
+  if (g_mll_impl < 0) {
+    const char* e = getenv("VOLT_MLL_IMPL");
+    g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
+  }
+  return g_mll_impl ? launch_mll_batched_tc(p, st) : launch_mll_batched_simt(p, st);
+}
+
 static MllParams base_params(int B, int T, const float* resid, const float* noise, int noise_stride, float jitter, int max_tries,
                              float* scalars, float* alpha, int* info) {
   MllParams p;
@@ -152,6 +163,11 @@ const char* volt_last_error(void) { return g_err; }
 int volt_abi_version(void) { return VOLT_ABI_VERSION; }
 int volt_device_check(void) { return device_check(); }
 long long volt_launch_count(void) { return g_launches; }
+int volt_set_mll_impl(int impl) {
+  const int prev = g_mll_impl;
+  g_mll_impl = impl ? 1 : 0;
+  return prev;
+}
 
 int volt_cumtrapz(const float* x, int x_batched, const float* y, int B, int T, int vol_mode, int half_last, float* V, void* stream) {
   VOLT_REQUIRE(x && y && V, "volt_cumtrapz: null pointer");

@@ -51,7 +51,9 @@ struct RolloutParams {
   int Hp;                  // padded tile row length (odd)
 };
 
-int launch_mll_batched(MllParams p, cudaStream_t st);
+int launch_mll_batched(MllParams p, cudaStream_t st);      // dispatches on the selected implementation
+int launch_mll_batched_simt(MllParams p, cudaStream_t st); // fp32 CUDA-core GEMM micro-kernel (chol_batched.cu)
+int launch_mll_batched_tc(MllParams p, cudaStream_t st);   // tcgen05 3xTF32 tensor-core products (chol_tc.cu)
 int launch_rollout(RolloutParams p, cudaStream_t st);
 int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kind, float theta, const float* latent, float* out,
                     float* e_out, float* ee_out, float* resid_out, cudaStream_t st);
