@@ -147,13 +147,187 @@ __device__ void trtri64(const float* Ct, float* LiT, float* tmpbuf) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- warp-level diagonal block
+// One warp factors and inverts the 64x64 diagonal block as a 2x2 grid of 32x32 blocks, one matrix row (or inverse
+// column) per lane held in registers, operands broadcast through small shared-memory panels (no block barriers):
+//   L11 = chol(S11); L21 = S21 L11^-T; S22 -= L21 L21^T; L22 = chol(S22);
+//   Li11 = L11^-1, Li22 = L22^-1 (one column per lane, forward substitution); Li21 = -Li22 (L21 Li11).
+// In/out: Ct (column-major, stride CLD; lower triangle valid on entry, L on exit), LiT[k][c] = Linv[c][k],
+// diagl[r] = L[r][r]; tmp: >= 3*32*DW_LD + 128 floats of scratch.  All 32 lanes of the calling warp must be active.
+constexpr int DW_LD = 36;  // row stride of the 32x32 broadcast panels (floats, 16-byte aligned rows)
+
+#define VOLT_CBAR() asm volatile("" ::: "memory")
+
+// sum_{t < N} row[t] * x[t] with four independent accumulators; `row` is a 16-byte aligned shared-memory row that
+// every lane reads at the same address (broadcast).  N is a compile-time constant after unrolling.
+template <int N>
+__device__ __forceinline__ float dot_bcast(const float* row, const float (&x)[32]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int t = 0; t < N; t += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + t);
+    s0 = fmaf(v.x, x[t], s0);
+    if (t + 1 < N) s1 = fmaf(v.y, x[t + 1], s1);
+    if (t + 2 < N) s2 = fmaf(v.z, x[t + 2], s2);
+    if (t + 3 < N) s3 = fmaf(v.w, x[t + 3], s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+// right-looking Cholesky of a 32x32 block, lane = row, a[k] = S[lane][k] (k <= lane valid).  colbuf: 64 floats.
+__device__ __forceinline__ void potrf32_warp(float (&a)[32], float* colbuf, int lane, int& failc, int off) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float d = __shfl_sync(0xffffffffu, a[c], c);
+    if (!(d > 0.f) && failc < 0) failc = off + c;
+    const float l = sqrtf(d);
+    const float inv = 1.f / l;
+    const float lrc = (lane == c) ? l : a[c] * inv;
+    a[c] = lrc;
+    float* cb = colbuf + (c & 1) * 32;
+    cb[lane] = lrc;
+    __syncwarp();
+#pragma unroll
+    for (int k4 = (c + 1) & ~3; k4 < 32; k4 += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(cb + k4);
+      if (k4 > c) a[k4] = fmaf(-lrc, v.x, a[k4]);
+      if (k4 + 1 > c) a[k4 + 1] = fmaf(-lrc, v.y, a[k4 + 1]);
+      if (k4 + 2 > c) a[k4 + 2] = fmaf(-lrc, v.z, a[k4 + 2]);
+      if (k4 + 3 > c) a[k4 + 3] = fmaf(-lrc, v.w, a[k4 + 3]);
+    }
+    VOLT_CBAR();
+  }
+}
+
+// forward substitution with the row-major lower-triangular panel Lp (stride DW_LD) and reciprocal diagonal invd:
+// x <- solution of (x' L^T = x) when UNIT_RHS == false (x holds the right-hand side), or column `lane` of L^-1 when
+// UNIT_RHS == true (x is overwritten).
+template <bool UNIT_RHS, int K>
+struct FwdSub {
+  static __device__ __forceinline__ void run(float (&x)[32], const float* Lp, const float* invd, int lane) {
+    FwdSub<UNIT_RHS, K - 1>::run(x, Lp, invd, lane);
+    constexpr int k = K - 1;
+    const float rhs = UNIT_RHS ? ((k == lane) ? 1.f : 0.f) : x[k];
+    const float acc = rhs - dot_bcast<k>(Lp + k * DW_LD, x);
+    x[k] = acc * invd[k];
+    VOLT_CBAR();
+  }
+};
+template <bool UNIT_RHS>
+struct FwdSub<UNIT_RHS, 0> {
+  static __device__ __forceinline__ void run(float (&)[32], const float*, const float*, int) {}
+};
+
+// y[r] = sum_{t < (TRI ? r+1 : 32)} P[r][t] * x[t] for r = 0..31 (P row-major, stride DW_LD, broadcast reads)
+template <bool TRI, int R>
+struct MatVec {
+  static __device__ __forceinline__ void run(float (&y)[32], const float* P, const float (&x)[32]) {
+    MatVec<TRI, R - 1>::run(y, P, x);
+    constexpr int r = R - 1;
+    y[r] = dot_bcast<(TRI ? r + 1 : 32)>(P + r * DW_LD, x);
+    VOLT_CBAR();
+  }
+};
+template <bool TRI>
+struct MatVec<TRI, 0> {
+  static __device__ __forceinline__ void run(float (&)[32], const float*, const float (&)[32]) {}
+};
+
+template <int CLD>
+__device__ void diag64_warp(float* Ct, float* LiT, float* tmp, float* diagl, int* flag, int col0) {
+  const int lane = threadIdx.x & 31;
+  float* P0 = tmp;                    // L11 (row-major), later L22
+  float* P1 = tmp + 32 * DW_LD;       // L21
+  float* P2 = tmp + 64 * DW_LD;       // Li22 (row-major)
+  float* colbuf = tmp + 96 * DW_LD;   // 64 floats
+  float* invd = colbuf + 64;          // 64 floats: 1 / L[r][r]
+  int failc = -1;
+  float a[32], x[32];
+
+  // ---- L11 = chol(S11)   (lane = row)
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = Ct[k * CLD + lane];
+  potrf32_warp(a, colbuf, lane, failc, 0);
+  {
+    float dl = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float v = (k <= lane) ? a[k] : 0.f;
+      dl = (k == lane) ? v : dl;
+      P0[lane * DW_LD + k] = v;
+      Ct[k * CLD + lane] = v;
+    }
+    diagl[lane] = dl;
+    invd[lane] = 1.f / dl;
+  }
+  __syncwarp();
+  // ---- L21 = S21 L11^-T  (lane = row 32 + lane)
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x[k] = Ct[k * CLD + 32 + lane];
+  FwdSub<false, 32>::run(x, P0, invd, lane);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    P1[lane * DW_LD + k] = x[k];
+    Ct[k * CLD + 32 + lane] = x[k];
+  }
+  // ---- Li11 (lane = column m): a[k] = Linv11[k][m]
+  FwdSub<true, 32>::run(a, P0, invd, lane);
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    *reinterpret_cast<float4*>(LiT + lane * CLD + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+    *reinterpret_cast<float4*>(LiT + (32 + lane) * CLD + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  // ---- S22 -= L21 L21^T ; L22 = chol(S22)   (lane = row 32 + lane; x = its L21 row)
+  MatVec<false, 32>::run(a, P1, x);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) a[k] = Ct[(32 + k) * CLD + 32 + lane] - a[k];
+  potrf32_warp(a, colbuf, lane, failc, 32);
+  __syncwarp();
+  {
+    float dl = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float v = (k <= lane) ? a[k] : 0.f;
+      dl = (k == lane) ? v : dl;
+      P0[lane * DW_LD + k] = v;
+      Ct[(32 + k) * CLD + 32 + lane] = v;
+    }
+    diagl[32 + lane] = dl;
+    invd[32 + lane] = 1.f / dl;
+  }
+  __syncwarp();
+  // ---- Li22 (lane = column m)
+  FwdSub<true, 32>::run(a, P0, invd + 32, lane);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) P2[k * DW_LD + lane] = a[k];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4)
+    *reinterpret_cast<float4*>(LiT + (32 + lane) * CLD + 32 + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+  __syncwarp();
+  // ---- Li21 = -Li22 (L21 Li11)   (lane = column m): x = Li11[:, m]; a = L21 x; x = Li22 a
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(LiT + lane * CLD + k);
+    x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+  }
+  MatVec<false, 32>::run(a, P1, x);
+  MatVec<true, 32>::run(x, P2, a);
+#pragma unroll
+  for (int k = 0; k < 32; k += 4)
+    *reinterpret_cast<float4*>(LiT + lane * CLD + 32 + k) = make_float4(-x[k], -x[k + 1], -x[k + 2], -x[k + 3]);
+  if (lane == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------- generator
 static __device__ __forceinline__ float gen_entry(const MllParams& p, int b, int i, int j, const float* Vs, float sc, float dadd) {
   if (i >= p.T || j >= p.T) return (i == j) ? 1.f : 0.f;
   float v;
   if (p.kind == KIND_VOL) v = Vs[min(i, j)];
   else if (p.kind == KIND_BM) v = sc * fminf(Vs[i], Vs[j]);
-  else v = (i >= j) ? p.dense[(size_t)b * p.dense_bstride + (size_t)i * p.ldd + j] : 0.f;
+  else v = (i >= j) ? p.dense[(size_t)b * p.dense_bstride + (size_t)i * p.ldd + j]
+                  : p.dense[(size_t)b * p.dense_bstride + (size_t)j * p.ldd + i];  // symmetric: only the lower triangle is read
   if (i == j) v += dadd;
   return v;
 }

@@ -26,7 +26,8 @@ constexpr uint32_t B_TILE = 64u * 128u;       // bytes of one 64-row x 32-float 
 // shared-memory map (byte offsets from a 1024-aligned base)
 constexpr uint32_t X_AHI = 0, X_ALO = A_TILE, X_BHI = 2 * A_TILE, X_BLO = 2 * A_TILE + B_TILE;
 constexpr uint32_t X_BYTES = 2 * A_TILE + 2 * B_TILE;           // 48 KB GEMM stage; aliased by P (hi|lo) and LiT|tmp
-constexpr uint32_t X_LIT = 0, X_TMP = 64 * CLD * 4;             // 17408 B + 16384 B <= 48 KB
+constexpr uint32_t X_LIT = 0, X_TMP = 64 * CLD * 4;             // LiT 17408 B, diag scratch 14336 B,
+constexpr uint32_t X_STASH = 32768;                             // 16 KB stash of the chunk-0 panel rows  (<= 48 KB)
 constexpr uint32_t L_OFF = X_BYTES;                             // Linv operand: hi k-tile0, hi k-tile1, lo k-tile0, lo k-tile1
 constexpr uint32_t L_BYTES = 4 * B_TILE;                        // 32 KB
 constexpr uint32_t CT_OFF = L_OFF + L_BYTES;                    // diagonal block, column-major, stride CLD
@@ -226,10 +227,9 @@ __device__ __forceinline__ void stage_linv_from_dinv(Ctx& c, const float* D) {
 }
 
 __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_tmem;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
+  if ((s_u32(smem_raw) & 1023u) != 0u) __trap();  // SWIZZLE_128B operand tiles need a 1024-byte aligned base
   Ctx c;
   c.X = base;
   c.Lr = base + L_OFF;
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   c.tmp = c.diagl + NB;
   c.red = c.tmp + 2 * NB;
   c.flag = reinterpret_cast<int*>(c.red + 32);
-  c.bar = &s_bar;
+  c.bar = reinterpret_cast<uint64_t*>(c.red + 36);
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 38);
   c.phase = 0;
   float* LiT = reinterpret_cast<float*>(c.X + X_LIT);
   float* tmpbuf = reinterpret_cast<float*>(c.X + X_TMP);
@@ -256,17 +257,17 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   float* dinv = p.dinv + (size_t)blockIdx.x * nb * NB * NB;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s_u32(s_tmem_p)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(c.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  c.tmem = s_tmem;
+  c.tmem = *s_tmem_p;
   const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -311,13 +312,20 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) s[q] = (gr < Tp) ? gen_entry(p, b, gr, R0 + c0 + q, c.Vs, sc, dadd) - s[q] : 0.f;
           if (ch == 0) {
+            // rows < 64 are the diagonal block (-> Ct); the other rows park their 32 values in the free tail of X so
+            // that no accumulator registers stay live across the warp-level factorisation below
+            float4* stash = reinterpret_cast<float4*>(c.X + X_STASH);
+            const int slot = (row - NB) + NB * half_id;
             if (row < NB) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) c.Ct[(c0 + q) * CLD + row] = s[q];
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
             __syncthreads();
-            potrf64<CLD>(c.Ct, c.diagl, c.flag, R0);
-            trtri64<CLD>(c.Ct, LiT, tmpbuf);
+            if (warp == 0) diag64_warp<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
+            __syncthreads();
             if (tid < NB && R0 + tid < T) logdet_part += logf(c.diagl[tid]);
             for (int idx = tid; idx < NB * NB; idx += NT) {
               const int r = idx >> 6, cc = idx & 63;
@@ -354,7 +362,17 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
                 (which ? c.z2 : c.z)[R0 + cc] = zz;
               }
             }
-            __syncthreads();  // LiT / tmp (aliasing X) are dead from here on; Linv operand staged
+            if (row >= NB) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 v = stash[q * 128 + slot];
+                s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) s[q] = 0.f;
+            }
+            __syncthreads();  // LiT / tmp / stash (aliasing X) are dead from here on; Linv operand staged
           }
           float o[32];
           trsm_tc(c, s, o, row, half_id);
@@ -392,7 +410,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
         if (tid < NB) {
           float a = 0.f;
           for (int cc = tid; cc < NB; ++cc) a = fmaf(Di[tid * NB + cc], c.z[R0 + cc], a);
-          atomicAdd(&c.al[R0 + tid], a);
+          c.al[R0 + tid] += a;
         }
         __syncthreads();
         const int nch = (R0 + CM - 1) / CM;
@@ -406,6 +424,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) s[q] = -s[q];
           trsm_tc(c, s, o, row, half_id);
+          float hdot = 0.f;
           if (m < R0) {
             float* dst = S + (size_t)m * ld + R0 + c0;
             float dot = 0.f;
@@ -417,8 +436,11 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
               if (m < T && R0 + c0 + q < T) tr_part = fmaf(o[q], o[q], tr_part);
               dot = fmaf(o[q], c.z[R0 + c0 + q], dot);
             }
-            atomicAdd(&c.al[m], dot);
+            if (half_id) c.tmp[row] = dot;   // the two column halves of a row are combined in a fixed order
+            else hdot = dot;
           }
+          __syncthreads();
+          if (m < R0 && half_id == 0) c.al[m] += hdot + c.tmp[row];
           __syncthreads();
         }
       }
@@ -475,7 +497,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.Tp = (p.T + NB - 1) / NB * NB;
   p.nb = p.Tp / NB;
-  const size_t smem = 1024 + tc::VEC_OFF + sizeof(float) * (size_t)(4 * p.Tp + NB + 2 * NB + 32 + 4);
+  const size_t smem = tc::VEC_OFF + sizeof(float) * (size_t)(4 * p.Tp + NB + 2 * NB + 32 + 8);
   if (smem > 227 * 1024) {
     set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);
     return VOLT_ERR_ARG;
