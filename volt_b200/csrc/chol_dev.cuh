@@ -320,6 +320,132 @@ __device__ void diag64_warp(float* Ct, float* LiT, float* tmp, float* diagl, int
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------- compact diagonal block
+// Block-cooperative factor + inverse of the 64x64 diagonal block with ROLLED loops (small code: the fully unrolled
+// warp version above is instruction-fetch bound) as a 2x2 grid of 32x32 blocks:
+//   warp 0: L11 = chol(S11) | warp 0: L21 = S21 L11^-T, warp 1: Li11 | all: S22 -= L21 L21^T |
+//   warp 0: L22 = chol(S22), warps 1-7: W^T = Li11^T-rows . L21-rows | warp 0: Li22 | all: Li21 = -Li22 W.
+// D: row-major diagonal block, stride RLD (lower triangle valid on entry; L with a zeroed strict upper triangle in
+// each 32x32 diagonal sub-block on exit).  LiT[k][c] = Linv[c][k] (stride RLD).  scratch: >= 2*32*36 + 32 + 64 floats.
+// Must be called by all threads of the CTA (contains __syncthreads).
+template <int RLD>
+__device__ __forceinline__ void potrf32_rolled(float* D, int o, float* colbuf, float* invd, float* diagl, int lane, int& failc) {
+  float* rowp = D + (o + lane) * RLD + o;
+  for (int c = 0; c < 32; ++c) {
+    const float d = D[(o + c) * RLD + o + c];
+    if (!(d > 0.f) && failc < 0) failc = o + c;
+    const float l = sqrtf(d);
+    const float inv = 1.f / l;
+    const float lrc = (lane == c) ? l : rowp[c] * inv;
+    if (lane >= c) rowp[c] = lrc; else rowp[c] = 0.f;
+    colbuf[lane] = lrc;
+    if (lane == c) { diagl[o + c] = l; invd[o + c] = inv; }
+    __syncwarp();
+    for (int k4 = (c + 1) & ~3; k4 < 32; k4 += 4) {
+      const float4 cb = *reinterpret_cast<const float4*>(colbuf + k4);
+      float4 own = *reinterpret_cast<float4*>(rowp + k4);
+      if (k4 > c) own.x = fmaf(-lrc, cb.x, own.x);
+      if (k4 + 1 > c) own.y = fmaf(-lrc, cb.y, own.y);
+      if (k4 + 2 > c) own.z = fmaf(-lrc, cb.z, own.z);
+      own.w = fmaf(-lrc, cb.w, own.w);
+      *reinterpret_cast<float4*>(rowp + k4) = own;
+    }
+    __syncwarp();
+  }
+}
+
+// x[k] <- (rhs_k - sum_{t<k} L[k][t] x[t]) * invd[k], k = 0..31; L row-major (stride RLD, zero above the diagonal),
+// x a private row per lane.  unit: rhs = e_lane (x must be zero-initialised), otherwise rhs = x[k] on entry.
+template <int RLD>
+__device__ __forceinline__ void fwdsub32_rolled(const float* L, float* x, const float* invd, bool unit, int lane) {
+  for (int k = 0; k < 32; ++k) {
+    const float* Lk = L + k * RLD;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int t4 = 0; t4 < k; t4 += 4) {
+      const float4 l4 = *reinterpret_cast<const float4*>(Lk + t4);
+      const float4 x4 = *reinterpret_cast<const float4*>(x + t4);
+      a0 = fmaf(l4.x, x4.x, a0);
+      if (t4 + 1 < k) a1 = fmaf(l4.y, x4.y, a1);
+      if (t4 + 2 < k) a2 = fmaf(l4.z, x4.z, a2);
+      if (t4 + 3 < k) a3 = fmaf(l4.w, x4.w, a3);
+    }
+    const float rhs = unit ? ((k == lane) ? 1.f : 0.f) : x[k];
+    x[k] = (rhs - ((a0 + a1) + (a2 + a3))) * invd[k];
+  }
+}
+
+__device__ __forceinline__ float dot32(const float* a, const float* b) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 32; t += 4) {
+    const float4 u = *reinterpret_cast<const float4*>(a + t);
+    const float4 v = *reinterpret_cast<const float4*>(b + t);
+    s0 = fmaf(u.x, v.x, s0); s1 = fmaf(u.y, v.y, s1); s2 = fmaf(u.z, v.z, s2); s3 = fmaf(u.w, v.w, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+constexpr int DIAG_SCRATCH_FLOATS = 2 * 32 * 36 + 32 + 64;
+
+template <int RLD>
+__device__ void diag64_block(float* D, float* LiT, float* scratch, float* diagl, int* flag, int col0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* Li22r = scratch;              // 32 x 36 row-major Li22
+  float* WT = scratch + 32 * 36;       // 32 x 36: WT[m][r] = (L21 Li11)[r][m]
+  float* colbuf = WT + 32 * 36;        // 32
+  float* invd = colbuf + 32;           // 64
+  int failc = -1;
+  // ---- S0: L11
+  if (warp == 0) potrf32_rolled<RLD>(D, 0, colbuf, invd, diagl, lane, failc);
+  else {
+    for (int i = tid - 32; i < 64 * 64; i += NT - 32) LiT[(i >> 6) * RLD + (i & 63)] = 0.f;
+    for (int i = tid - 32; i < 32 * 36; i += NT - 32) Li22r[i] = 0.f;
+  }
+  __syncthreads();
+  // ---- S1: L21 (warp 0)  ||  Li11 (warp 1)
+  if (warp == 0) fwdsub32_rolled<RLD>(D, D + (32 + lane) * RLD, invd, false, lane);
+  else if (warp == 1) fwdsub32_rolled<RLD>(D, LiT + lane * RLD, invd, true, lane);
+  __syncthreads();
+  // ---- S2: S22 -= L21 L21^T (lower part only)
+  {
+    const int r = tid >> 3, k0 = (tid & 7) * 4;
+    if (k0 <= r) {
+      const float* xr = D + (32 + r) * RLD;
+      float* out = D + (32 + r) * RLD + 32 + k0;
+      float4 o4 = *reinterpret_cast<float4*>(out);
+      o4.x -= dot32(xr, D + (32 + k0) * RLD);
+      o4.y -= dot32(xr, D + (33 + k0) * RLD);
+      o4.z -= dot32(xr, D + (34 + k0) * RLD);
+      o4.w -= dot32(xr, D + (35 + k0) * RLD);
+      *reinterpret_cast<float4*>(out) = o4;
+    }
+  }
+  __syncthreads();
+  // ---- S3: L22 (warp 0)  ||  WT (warps 1..7)
+  if (warp == 0) potrf32_rolled<RLD>(D, 32, colbuf, invd, diagl, lane, failc);
+  else {
+    for (int i = tid - 32; i < 32 * 32; i += NT - 32) {
+      const int m = i >> 5, r = i & 31;
+      WT[m * 36 + r] = dot32(LiT + m * RLD, D + (32 + r) * RLD);
+    }
+  }
+  __syncthreads();
+  // ---- S4: Li22 (warp 0): column `lane` -> LiT row 32+lane (cols 32..63) and the row-major copy Li22r
+  if (warp == 0) {
+    float* y = LiT + (32 + lane) * RLD + 32;
+    fwdsub32_rolled<RLD>(D + 32 * RLD + 32, y, invd + 32, true, lane);
+    for (int k = 0; k < 32; ++k) Li22r[k * 36 + lane] = y[k];
+    if (lane == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
+  }
+  __syncthreads();
+  // ---- S5: Li21 = -Li22 (L21 Li11): LiT[m][32 + r] = -sum_t Li22r[r][t] WT[m][t]
+  for (int i = tid; i < 32 * 32; i += NT) {
+    const int m = i >> 5, r = i & 31;
+    LiT[m * RLD + 32 + r] = -dot32(Li22r + r * 36, WT + m * 36);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------- generator
 static __device__ __forceinline__ float gen_entry(const MllParams& p, int b, int i, int j, const float* Vs, float sc, float dadd) {
   if (i >= p.T || j >= p.T) return (i == j) ? 1.f : 0.f;

@@ -30,7 +30,7 @@ constexpr uint32_t X_LIT = 0, X_TMP = 64 * CLD * 4;             // LiT 17408 B, 
 constexpr uint32_t X_STASH = 32768;                             // 16 KB stash of the chunk-0 panel rows  (<= 48 KB)
 constexpr uint32_t L_OFF = X_BYTES;                             // Linv operand: hi k-tile0, hi k-tile1, lo k-tile0, lo k-tile1
 constexpr uint32_t L_BYTES = 4 * B_TILE;                        // 32 KB
-constexpr uint32_t CT_OFF = L_OFF + L_BYTES;                    // diagonal block, column-major, stride CLD
+constexpr uint32_t CT_OFF = L_OFF + L_BYTES;                    // diagonal block D, row-major, stride CLD
 constexpr uint32_t CT_BYTES = 64 * CLD * 4;
 constexpr uint32_t VEC_OFF = CT_OFF + CT_BYTES;
 
@@ -318,18 +318,18 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
             const int slot = (row - NB) + NB * half_id;
             if (row < NB) {
 #pragma unroll
-              for (int q = 0; q < 32; ++q) c.Ct[(c0 + q) * CLD + row] = s[q];
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             } else {
 #pragma unroll
               for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
             __syncthreads();
-            if (warp == 0) diag64_warp<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
-            __syncthreads();
+            diag64_block<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
             if (tid < NB && R0 + tid < T) logdet_part += logf(c.diagl[tid]);
             for (int idx = tid; idx < NB * NB; idx += NT) {
               const int r = idx >> 6, cc = idx & 63;
-              S[(size_t)(R0 + r) * ld + R0 + cc] = (cc <= r) ? c.Ct[cc * CLD + r] : 0.f;
+              S[(size_t)(R0 + r) * ld + R0 + cc] = (cc <= r) ? c.Ct[r * CLD + cc] : 0.f;
               dinv[((size_t)j * NB + r) * NB + cc] = LiT[r * CLD + cc];
             }
             stage_linv_from_lit(c, LiT);
