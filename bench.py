@@ -270,9 +270,9 @@ def main():
         gpu_launches=int(launches),
         clocks=clocks,
         roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=None,
-                      kernel="mll_batched_kernel", ms_per_launch=kern_ms, bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
+                      kernel="mll_batched_tc_kernel (+ cumtrapz_kernel, <1% of the time)", ms_per_launch=kern_ms, bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
         roofline_tensor=dict(bound="tensor", achieved=ach_tf, peak=pk["tf"], unit="TFLOP/s", frac=ach_tf / pk["tf"],
-                             flops_per_eval=flops_per_eval, note="fp32 SIMT path; peak is the measured bf16 GEMM figure"),
+                             flops_per_eval=flops_per_eval, note="tcgen05 kind::tf32 3-pass split (hi*hi + hi*lo + lo*hi): 3x the algorithmic flops are issued on the tensor pipe; peak is the measured bf16 dense GEMM figure (nominal TF32 peak is half of bf16)"),
     )
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
