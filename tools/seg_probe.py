@@ -1,4 +1,4 @@
-import sys, os, ctypes
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from volt_b200 import _lib
@@ -10,11 +10,6 @@ _, resid = ops.ma_mean("ewma", logy.cuda(), 25, want_resid=True)
 raw = torch.full((B,), 1e-5).cuda()
 for _ in range(3): out = batched.mll_and_grad(x.cuda(), vol.cuda(), resid, raw)
 torch.cuda.synchronize()
-a = out["alpha"].reshape(-1)[:48].cpu().reshape(4, 12)
-names = ["other/storeprev", "gemmA", "epiA(ld+gen)", "stash", "diag64", "diagpost(L,dinv,linv,z)", "trsmA", "storeB+loop", "gemmB", "trsmB", "phaseB tail", "final"]
-tot = a.sum(1)
-for i, n in enumerate(names):
-    print(f"{n:28s} " + "  ".join(f"{a[c, i]/1e3:9.0f}k ({100*a[c,i]/tot[c]:4.1f}%)" for c in range(4)))
-print("total cycles", tot.tolist())
-g = out["alpha"].reshape(-1)[48:54].cpu()
-print("gemm_tc producer thread 32 (CTA 0, kcycles): other %.0f wait_stage %.0f st_split(+load wait) %.0f gload-issue %.0f fence %.0f arrive %.0f" % tuple((g / 1e3).tolist()))
+a = out["alpha"].reshape(-1)[:12].cpu()
+names = ["non-diag", "S0 potrf11(+zero)", "S1 trsm||Li11", "S2 syrk", "S3 potrf22||WT", "S4 Li22", "S5 Li21", "(after diag)", "rest"]
+for n, v in zip(names, a.tolist()): print(f"{n:22s} {v/1e3:9.0f}k cycles  ({v/32/1e3:6.1f}k per diag block)")

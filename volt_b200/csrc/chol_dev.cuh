@@ -446,6 +446,156 @@ __device__ void diag64_block(float* D, float* LiT, float* scratch, float* diagl,
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------- blocked diagonal block (v2)
+// 64x64 factor + inverse as 4 panels of 16 columns.  The 16x16 pivot block is factored AND inverted by one warp
+// entirely in registers (row / inverse column per lane, operands exchanged with shuffles: no shared-memory round
+// trips on the 16-step dependency chain); the panel solve, the trailing update and the off-diagonal blocks of the
+// inverse are small products spread over all 256 threads with rolled loops.  Measured: the 32x32 smem-resident
+// version above spends ~700 cycles per elimination step; this one ~100.
+// D: row-major, stride RLD (lower triangle valid on entry; L in the lower triangle on exit, upper part untouched).
+// LiT[k][c] = Linv[c][k] (stride RLD).  scratch: >= DIAG2_SCRATCH_FLOATS floats.  All CTA threads must call it.
+constexpr int I16_LD = 20;
+constexpr int DIAG2_SCRATCH_FLOATS = 4 * 16 * I16_LD + 48 * 20 + 64;
+
+template <int RLD>
+__device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, float* diagl, int o, int lane, int& failc) {
+  const int r = lane & 15;
+  float a[16], inv16[16];
+  {
+    const float4* src = reinterpret_cast<const float4*>(D + (o + r) * RLD + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = src[q];
+      a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float d = __shfl_sync(0xffffffffu, a[c], c);
+    if (!(d > 0.f) && failc < 0) failc = o + c;
+    float inv = rsqrtf(d);
+    inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);  // one Newton step: 1/sqrt(d) to ~1 ulp
+    const float l = d * inv;
+    inv16[c] = inv;
+    const float lrc = (r == c) ? l : a[c] * inv;
+    a[c] = lrc;
+#pragma unroll
+    for (int k = c + 1; k < 16; ++k) a[k] = fmaf(-lrc, __shfl_sync(0xffffffffu, lrc, k), a[k]);
+  }
+  if (lane < 16) {
+    float dl = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dl = (k == r) ? a[k] : dl;
+    diagl[o + r] = dl;
+    float4* dst = reinterpret_cast<float4*>(D + (o + r) * RLD + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dst[q] = make_float4(4 * q <= r ? a[4 * q] : 0.f, 4 * q + 1 <= r ? a[4 * q + 1] : 0.f, 4 * q + 2 <= r ? a[4 * q + 2] : 0.f,
+                           4 * q + 3 <= r ? a[4 * q + 3] : 0.f);
+  }
+  // inverse: lane = column m, y[k] = Linv16[k][m]
+  float y[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float acc = (k == r) ? 1.f : 0.f;
+#pragma unroll
+    for (int t = 0; t < k; ++t) acc = fmaf(-__shfl_sync(0xffffffffu, a[t], k), y[t], acc);
+    y[k] = acc * inv16[k];
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) I16p[k * I16_LD + r] = y[k];
+    float4* dst = reinterpret_cast<float4*>(LiT + (o + r) * RLD + o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+  }
+}
+
+__device__ __forceinline__ float dotn(const float* a, const float* b, int n) {  // n multiple of 4, 16-byte aligned
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int t = 0; t < n; t += 4) {
+    const float4 u = *reinterpret_cast<const float4*>(a + t);
+    const float4 v = *reinterpret_cast<const float4*>(b + t);
+    s0 = fmaf(u.x, v.x, s0); s1 = fmaf(u.y, v.y, s1); s2 = fmaf(u.z, v.z, s2); s3 = fmaf(u.w, v.w, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+template <int RLD>
+__device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* diagl, int* flag, int col0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* I16 = scratch;                          // 4 x (16 x I16_LD): row-major inverses of the pivot blocks
+  float* XP = scratch + 4 * 16 * I16_LD;         // 48 x 20: solved panel rows (row-major, 16 columns)
+  int failc = -1;
+  for (int p = 0; p < 4; ++p) {
+    const int o = 16 * p;
+    const int R = 48 - o;                        // rows below the pivot block
+    // ---- P1: pivot block (warp 0); the other warps clear LiT once
+    if (warp == 0) pivot16_warp<RLD>(D, LiT, I16 + p * 16 * I16_LD, diagl, o, lane, failc);
+    else if (p == 0) {
+      for (int i = tid - 32; i < 64 * 64; i += NT - 32) {
+        const int k = i >> 6, cc = i & 63;
+        if ((k >> 4) != (cc >> 4)) LiT[k * RLD + cc] = 0.f;   // diagonal 16-blocks are written by the pivot warps
+      }
+    }
+    __syncthreads();
+    if (R > 0) {
+      // ---- P2: panel solve X = S_panel Linv16^T (thread per (row, 4 columns); rows read before anybody writes)
+      const float* Ip = I16 + p * 16 * I16_LD;
+      for (int task = tid; task < R * 4; task += NT) {
+        const int rr = task >> 2, cq = (task & 3) * 4;
+        const float* srow = D + (o + 16 + rr) * RLD + o;
+        float4 out;
+        out.x = dotn(srow, Ip + (cq + 0) * I16_LD, 16);
+        out.y = dotn(srow, Ip + (cq + 1) * I16_LD, 16);
+        out.z = dotn(srow, Ip + (cq + 2) * I16_LD, 16);
+        out.w = dotn(srow, Ip + (cq + 3) * I16_LD, 16);
+        *reinterpret_cast<float4*>(XP + rr * 20 + cq) = out;
+      }
+      __syncthreads();
+      // ---- P3: write the panel back and apply the trailing update D[r][c] -= X[r].X[c] (c <= r)
+      for (int task = tid; task < R * 4; task += NT) {
+        const int rr = task >> 2, cq = (task & 3) * 4;
+        *reinterpret_cast<float4*>(D + (o + 16 + rr) * RLD + o + cq) = *reinterpret_cast<const float4*>(XP + rr * 20 + cq);
+      }
+      for (int task = tid; task < R * (R / 4); task += NT) {
+        const int rr = task / (R / 4), cq = (task - rr * (R / 4)) * 4;
+        if (cq <= rr) {
+          float4* dst = reinterpret_cast<float4*>(D + (o + 16 + rr) * RLD + o + 16 + cq);
+          float4 v = *dst;
+          const float* xr = XP + rr * 20;
+          v.x -= dotn(xr, XP + (cq + 0) * 20, 16);
+          v.y -= dotn(xr, XP + (cq + 1) * 20, 16);
+          v.z -= dotn(xr, XP + (cq + 2) * 20, 16);
+          v.w -= dotn(xr, XP + (cq + 3) * 20, 16);
+          *dst = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
+  // ---- inverse: off-diagonal 16-blocks by block distance d = pb - qb.
+  //   W[r][c] = sum_{k in [16 qb, 16 pb)} L[16 pb + r][k] Linv[k][16 qb + c]  (= D row . LiT row, both contiguous)
+  //   Linv[16 pb + r][16 qb + c] = - sum_k Linv16_pb[r][k] W[k][c]
+  float* WT = XP;  // reuse: per block (16 x 20), WT[c][k] = W[k][c]; 3 blocks at most per level -> 48 x 20
+  for (int d = 1; d < 4; ++d) {
+    const int nblk = 4 - d;
+    for (int task = tid; task < nblk * 256; task += NT) {
+      const int bi = task >> 8, r = (task >> 4) & 15, cc = task & 15;
+      const int qb = bi, pb = bi + d;
+      WT[(bi * 16 + cc) * 20 + r] = dotn(D + (16 * pb + r) * RLD + 16 * qb, LiT + (16 * qb + cc) * RLD + 16 * qb, 16 * d);
+    }
+    __syncthreads();
+    for (int task = tid; task < nblk * 256; task += NT) {
+      const int bi = task >> 8, cc = (task >> 4) & 15, r = task & 15;
+      const int qb = bi, pb = bi + d;
+      LiT[(16 * qb + cc) * RLD + 16 * pb + r] = -dotn(I16 + pb * 16 * I16_LD + r * I16_LD, WT + (bi * 16 + cc) * 20, 16);
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- generator
 static __device__ __forceinline__ float gen_entry(const MllParams& p, int b, int i, int j, const float* Vs, float sc, float dadd) {
   if (i >= p.T || j >= p.T) return (i == j) ? 1.f : 0.f;

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
               for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
             __syncthreads();
-            diag64_block<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
+            diag64_block_v2<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
             if (tid < NB && R0 + tid < T) logdet_part += logf(c.diagl[tid]);
             for (int idx = tid; idx < NB * NB; idx += NT) {
               const int r = idx >> 6, cc = idx & 63;
