@@ -226,6 +226,46 @@ __device__ __forceinline__ void stage_linv_from_dinv(Ctx& c, const float* D) {
   }
 }
 
+// A-generator for one accumulator row: s[q] <- A[gr][gc0 + q] - s[q], q = 0..31.  Fast path (no identity padding, on-the-fly
+// kernels): the 32 column values come from 8 broadcast LDS.128 of the staged prefix vector.
+__device__ __forceinline__ void gen_sub_row32(const MllParams& p, int b, int gr, int gc0, const float* Vs, float sc, float dadd,
+                                              float (&s)[32]) {
+  if (p.kind != KIND_DENSE && p.T == p.Tp) {
+    const float vr = Vs[gr];
+    const bool vol = (p.kind == KIND_VOL);
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      const float4 cv = *reinterpret_cast<const float4*>(Vs + gc0 + 4 * q4);
+      const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gc = gc0 + 4 * q4 + e;
+        float v = vol ? ((gc <= gr) ? c4[e] : vr) : sc * fminf(vr, c4[e]);
+        if (gc == gr) v += dadd;
+        s[4 * q4 + e] = v - s[4 * q4 + e];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s[q] = gen_entry(p, b, gr, gc0 + q, Vs, sc, dadd) - s[q];
+  }
+}
+
+// Coalesced store of a warp's 32 x 32 block (lane = row, 32 columns in registers): transposed through a private
+// 32 x 36 float shared-memory tile so that every STG.128 writes 4 full 128-byte rows instead of 32 row fragments.
+__device__ __forceinline__ void store_block32(float* xs, const float (&o)[32], float* gdst /* row 0, col 0 of the block */, int ld,
+                                              int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(xs + lane * 36 + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i, ch = (lane & 7) * 4;
+    *reinterpret_cast<float4*>(gdst + (size_t)r * ld + ch) = *reinterpret_cast<const float4*>(xs + r * 36 + ch);
+  }
+}
+
 __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
@@ -309,8 +349,12 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) s[q] = 0.f;
           }
+          if (gr < Tp) {
+            gen_sub_row32(p, b, gr, R0 + c0, c.Vs, sc, dadd, s);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) s[q] = (gr < Tp) ? gen_entry(p, b, gr, R0 + c0 + q, c.Vs, sc, dadd) - s[q] : 0.f;
+            for (int q = 0; q < 32; ++q) s[q] = 0.f;
+          }
           if (ch == 0) {
             // rows < 64 are the diagonal block (-> Ct); the other rows park their 32 values in the free tail of X so
             // that no accumulator registers stay live across the warp-level factorisation below
@@ -376,11 +420,11 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
           }
           float o[32];
           trsm_tc(c, s, o, row, half_id);
-          if (!(ch == 0 && row < NB) && gr < Tp) {
-            float* dst = S + (size_t)gr * ld + R0 + c0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          {
+            // warp-uniform: the warp's 32 rows start at a multiple of 32 and Tp, R0 are multiples of 64
+            const int g0 = r_base + 32 * (warp & 3);
+            if (!(ch == 0 && (warp & 3) < 2) && g0 < Tp)
+              store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
           }
           __syncthreads();
         }
@@ -425,12 +469,12 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
           for (int q = 0; q < 32; ++q) s[q] = -s[q];
           trsm_tc(c, s, o, row, half_id);
           float hdot = 0.f;
+          {
+            const int g0 = m_base + 32 * (warp & 3);
+            if (g0 < R0) store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+          }
           if (m < R0) {
-            float* dst = S + (size_t)m * ld + R0 + c0;
             float dot = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               if (m < T && R0 + c0 + q < T) tr_part = fmaf(o[q], o[q], tr_part);
