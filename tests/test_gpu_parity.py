@@ -384,3 +384,18 @@ def test_full_size_c3_shape(vb):
     ref = O.volt_mll_and_grad(x, vol[3], resid[3].cpu(), raw[3].cpu())
     assert relerr(out["mll"][3], ref["mll"]) < 1e-4
     assert relerr(out["draw_noise"][3], ref["draw_noise"]) < 2e-3
+
+
+@pytest.mark.parametrize("T", [2048, 4096, 8192])
+def test_long_series_c5_shape(vb, T):
+    """BASELINE config 5 shape (one long series, T up to 8192) through the same tcgen05 blocked-Cholesky kernel
+    (one CTA per series at this size: functional, not yet the multi-CTA roofline point -- DESIGN.md section 8)."""
+    x, vol, logy = vb.batched.synth_series(1, T)
+    _, resid = vb.ops.ma_mean("ewma", logy.cuda(), 25, want_resid=True)
+    raw = torch.tensor([1e-5]).cuda()
+    out = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid, raw, check=True)
+    ref = O.volt_mll_and_grad(x.double(), vol[0].double(), resid[0].cpu().double(), raw[0].cpu().double())
+    assert relerr(out["mll"][0], ref["mll"]) < 1e-4
+    assert relerr(out["draw_noise"][0], ref["draw_noise"]) < 2e-3
+    assert relerr(out["alpha"][0], ref["alpha"]) < 2e-3
+    assert relerr(out["scalars"][0, 2], ref["logdet"]) < 1e-4

@@ -277,8 +277,9 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   c.Vs = reinterpret_cast<float*>(base + VEC_OFF);
   c.z = c.Vs + p.Tp;
   c.al = c.z + p.Tp;
-  c.z2 = c.al + p.Tp;
-  c.diagl = c.z2 + p.Tp;
+  const bool has2 = (p.resid2 != nullptr);   // the second right-hand side (rollout prep) gets its own vector
+  c.z2 = has2 ? c.al + p.Tp : c.z;
+  c.diagl = c.al + (has2 ? 2 : 1) * p.Tp;
   c.tmp = c.diagl + NB;
   c.red = c.tmp + 2 * NB;
   c.flag = reinterpret_cast<int*>(c.red + 32);
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
       const float dadd = dadd0 + jit_used;
       logdet_part = 0.f;
       if (tid == 0) *c.flag = -1;
-      for (int i = tid; i < Tp; i += NT) { c.z[i] = 0.f; c.al[i] = 0.f; c.z2[i] = 0.f; }
+      for (int i = tid; i < Tp; i += NT) { c.z[i] = 0.f; c.al[i] = 0.f; if (has2) c.z2[i] = 0.f; }
       __syncthreads();
       fail = 0;
       // =============================== Phase A
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
                 c.tmp[NB + cz] = ((rb2 && R0 + cz < T) ? rb2[R0 + cz] : 0.f) - a2;
               }
               __syncthreads();
-              if (tid < 2 * NB) {
+              if (tid < (has2 ? 2 : 1) * NB) {
                 const int cc = tid & 63, which = tid >> 6;
                 float zz = 0.f;
                 for (int k = 0; k <= cc; ++k) zz = fmaf(LiT[k * CLD + cc], c.tmp[which * NB + k], zz);
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
     // =============================== reductions and outputs (identical to the SIMT kernel)
     float zz = 0.f, aa = 0.f, ar = 0.f, z22 = 0.f, z12 = 0.f;
     for (int i = tid; i < T; i += NT) {
-      const float zi = c.z[i], ai = c.al[i], z2i = c.z2[i];
+      const float zi = c.z[i], ai = c.al[i], z2i = has2 ? c.z2[i] : 0.f;
       zz = fmaf(zi, zi, zz);
       z22 = fmaf(z2i, z2i, z22);
       z12 = fmaf(zi, z2i, z12);
