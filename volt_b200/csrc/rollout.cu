@@ -110,16 +110,21 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   float* ytail = sw + k;                // k
   float* etail = ytail + k;             // k+1
   float* eetail = etail + (k + 1);      // k+1
+  // staging tiles: only the ones this mean family / eps mode needs are allocated (launch_rollout sizes smem alike)
+  const bool ma = p.mean_kind != MA_GIVEN;
+  const bool need_ee = (p.mean_kind == MA_DEWMA || p.mean_kind == MA_TEWMA);
+  const bool need_e = need_ee || p.mean_kind == MA_MEANREVERT;
   float* t_pv = eetail + (k + 1);       // TS*Hp
-  float* t_eps = t_pv + TS * Hp;
-  float* t_out = t_eps + TS * Hp;
-  float* t_e = t_out + TS * Hp;         // e history  (per draw, index a -> e[n+1+a])
-  float* t_ee = t_e + TS * Hp;          // ee history
+  float* t_out = t_pv + TS * Hp;
+  float* nxt = t_out + TS * Hp;
+  float* t_eps = nxt;                   // base normals (absent with in-kernel Philox)
+  if (p.eps) nxt += TS * Hp;
+  float* t_e = nxt;                     // e history  (per draw, index a -> e[n+1+a])
+  if (need_e) nxt += TS * Hp;
+  float* t_ee = nxt;                    // ee history
   const int b = blockIdx.y;
   const int s0 = blockIdx.x * TS;
   const int tid = threadIdx.x;
-  const bool ma = p.mean_kind != MA_GIVEN;
-  const bool need_ee = (p.mean_kind == MA_DEWMA || p.mean_kind == MA_TEWMA);
 
   for (int t = tid; t < k; t += TS) sw[t] = p.w ? p.w[t] : 0.f;
   const float* yb = p.ytrain + (size_t)b * n;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
             }
             if (idx >= 1) eeh[idx - 1] = ee_m;  // ee[n+idx]
           }
-          if (idx >= 1) eh[idx - 1] = e_m;      // e[n+idx]
+          if (need_e && idx >= 1) eh[idx - 1] = e_m;      // e[n+idx]
         } else {
           m_test = p.mean_test ? p.mean_test[(size_t)b * H + idx] : 0.f;
         }
@@ -296,8 +301,11 @@ int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kin
 int launch_rollout(RolloutParams p, cudaStream_t st) {
   p.Hp = p.H | 1;
   int TS = 128;
-  auto smem_for = [&](int ts) { return sizeof(float) * ((size_t)4 * p.k + 2 + (size_t)5 * ts * p.Hp); };
-  while (TS > 32 && smem_for(TS) > 200 * 1024) TS >>= 1;
+  const bool need_ee = (p.mean_kind == MA_DEWMA || p.mean_kind == MA_TEWMA);
+  const bool need_e = need_ee || p.mean_kind == MA_MEANREVERT;
+  const int ntiles = 2 + (p.eps ? 1 : 0) + (need_e ? 1 : 0) + (need_ee ? 1 : 0);
+  auto smem_for = [&](int ts) { return sizeof(float) * ((size_t)4 * p.k + 2 + (size_t)ntiles * ts * p.Hp); };
+  while (TS > 32 && smem_for(TS) > 56 * 1024) TS >>= 1;   // aim for >= 4 resident CTAs per SM
   const size_t smem = smem_for(TS);
   if (smem > 220 * 1024) {
     set_error("rollout: H=%d, k=%d exceeds shared memory", p.H, p.k);
