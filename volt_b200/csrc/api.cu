@@ -130,6 +130,14 @@ int launch_mll_batched(MllParams p, cudaStream_t st) {
     const char* e = getenv("VOLT_MLL_IMPL");
     g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
   }
+  // A few very long series: one CTA per series would leave the GPU idle -> multi-CTA right-looking path, series by series.
+  if (g_mll_impl && p.resid && !p.resid2 && !p.L_out && !p.z_out && p.T >= 1536 && p.B <= 16) {
+    for (int b = 0; b < p.B; ++b) {
+      int s = launch_mll_large(p, b, st);
+      if (s) return s;
+    }
+    return VOLT_OK;
+  }
   return g_mll_impl ? launch_mll_batched_tc(p, st) : launch_mll_batched_simt(p, st);
 }
 

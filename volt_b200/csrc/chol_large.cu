@@ -1,0 +1,329 @@
+// Multi-CTA exact MLL + gradient for ONE long series (BASELINE config c5: T = 8192): right-looking blocked Cholesky
+// and a right-looking inverse sweep, every step a set of independent 128x64 tiles spread over all SMs, the K = 64
+// products on the tensor cores (tcgen05 kind::tf32, 3-pass hi/lo split) through the same building blocks as the
+// batched kernel (chol_tc_dev.cuh).
+//
+//   W  (Tp x Tp): lower triangle = A, overwritten by L            Ut (Tp x Tp): upper triangle = R^T, overwritten by (L^-1)^T
+//   for j:  diag   L_jj = chol(W_jj), Linv_jj, z_j = Linv_jj r_j                               (1 CTA)
+//           panel  W[i,j] <- W[i,j] Linv_jj^T (i > j),  r_i -= W[i,j] z_j                      ((T-R0)/128 CTAs)
+//           update W[i,c] -= W[i,j] W[c,j]^T  (j < c <= i)                                      (tiles)
+//   for k:  final  Ut[0:k+1, k] <- Ut[0:k+1, k] Linv_kk^T;  tr += |.|^2, alpha += (.) z_k       ((k+1)/2 CTAs)
+//           update Ut[n, i] -= Ut[n, k] W[i, k]^T  (n <= k < i)                                  (tiles)
+// Replaces the same reference call chain as chol_tc.cu (train_utils.py:247-250) when a single series is too long for
+// one CTA to be a sensible unit of work.
+#include "chol_tc_dev.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace volt {
+namespace large {
+
+using namespace tc;
+
+struct LargeParams {
+  int T, Tp, nb, kind;
+  const float* V;      // (T) cumtrapz prefix (KIND_VOL) or grid x (KIND_BM)
+  const float* dense;  // (T, ldd) KIND_DENSE
+  int ldd;
+  float scale, dadd;
+  const float* resid;  // (T)
+  float* W; float* Ut; float* dinv;
+  float* z;            // (Tp): residual, overwritten by z = L^-1 r
+  float* alpha;        // (Tp)
+  float* acc;          // [0] sum log L_ii, [1] tr(A^-1)
+  int* flag;           // first failing pivot index, -1 = none
+};
+
+__device__ __forceinline__ float gen_large(const LargeParams& p, int i, int j) {
+  if (i >= p.T || j >= p.T) return (i == j) ? 1.f : 0.f;
+  float v;
+  if (p.kind == KIND_VOL) v = p.V[min(i, j)];
+  else if (p.kind == KIND_BM) v = p.scale * fminf(p.V[i], p.V[j]);
+  else v = (i >= j) ? p.dense[(size_t)i * p.ldd + j] : p.dense[(size_t)j * p.ldd + i];
+  if (i == j) v += p.dadd;
+  return v;
+}
+
+// lower triangle of A -> W, residual -> z, alpha = 0, Ut = I (Ut is memset to 0 by the host first)
+__global__ void __launch_bounds__(256) large_build_kernel(LargeParams p) {
+  const int i = blockIdx.x;
+  float* row = p.W + (size_t)i * p.Tp;
+  for (int j = threadIdx.x; j <= i; j += 256) row[j] = gen_large(p, i, j);
+  if (threadIdx.x == 0) {
+    p.z[i] = (i < p.T) ? p.resid[i] : 0.f;
+    p.alpha[i] = 0.f;
+    p.Ut[(size_t)i * p.Tp + i] = 1.f;
+    if (i == 0) { p.acc[0] = 0.f; p.acc[1] = 0.f; *p.flag = -1; }
+  }
+}
+
+struct Shared {
+  Ctx c;
+  float* LiT; float* tmpbuf;
+};
+
+// common prologue: carve shared memory like the batched kernel, allocate TMEM, init the mbarrier
+__device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_tmem) {
+  Ctx& c = sh.c;
+  c.X = base;
+  c.Lr = base + L_OFF;
+  c.Ct = reinterpret_cast<float*>(base + CT_OFF);
+  c.Vs = reinterpret_cast<float*>(base + VEC_OFF);
+  c.z = c.Vs; c.al = c.Vs; c.z2 = c.Vs;
+  c.diagl = c.Vs;                 // 64
+  c.tmp = c.diagl + NB;           // 128
+  c.red = c.tmp + 2 * NB;         // 32
+  c.flag = reinterpret_cast<int*>(c.red + 32);
+  c.bar = reinterpret_cast<uint64_t*>(c.red + 36);
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 38);
+  c.phase = 0;
+  sh.LiT = reinterpret_cast<float*>(c.X + X_LIT);
+  sh.tmpbuf = reinterpret_cast<float*>(c.X + X_TMP);
+  if ((s_u32(base) & 1023u) != 0u) __trap();
+  if (need_tmem) {
+    if (threadIdx.x < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s_u32(s_tmem_p)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+      mbar_init(c.bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    c.tmem = *s_tmem_p;
+  }
+}
+__device__ __forceinline__ void cta_teardown(Shared& sh) {
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(sh.c.tmem) : "memory");
+}
+constexpr size_t LARGE_SMEM = VEC_OFF + sizeof(float) * (NB + 2 * NB + 32 + 12);
+
+// ---- diagonal block of step j (one CTA)
+__global__ void __launch_bounds__(NT, 1) large_diag_kernel(LargeParams p, int j) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Shared sh;
+  cta_setup(sh, smem_raw, false);
+  Ctx& c = sh.c;
+  const int tid = threadIdx.x, R0 = j * NB, ld = p.Tp;
+  for (int idx = tid; idx < NB * NB; idx += NT) {
+    const int r = idx >> 6, cc = idx & 63;
+    c.Ct[r * CLD + cc] = p.W[(size_t)(R0 + r) * ld + R0 + cc];
+  }
+  if (tid == 0) *c.flag = -1;
+  __syncthreads();
+  diag64_block_v2<CLD>(c.Ct, sh.LiT, sh.tmpbuf, c.diagl, c.flag, R0);
+  float* dj = p.dinv + (size_t)j * NB * NB;
+  for (int idx = tid; idx < NB * NB; idx += NT) {
+    const int r = idx >> 6, cc = idx & 63;
+    p.W[(size_t)(R0 + r) * ld + R0 + cc] = (cc <= r) ? c.Ct[r * CLD + cc] : 0.f;
+    dj[idx] = sh.LiT[r * CLD + cc];
+  }
+  if (tid < NB) c.tmp[tid] = p.z[R0 + tid];
+  __syncthreads();
+  if (tid < NB) {
+    float zz = 0.f;
+    for (int k = 0; k <= tid; ++k) zz = fmaf(sh.LiT[k * CLD + tid], c.tmp[k], zz);
+    p.z[R0 + tid] = zz;
+  }
+  float lg = (tid < NB && R0 + tid < p.T) ? logf(c.diagl[tid]) : 0.f;
+  lg = block_sum(lg, c.red);
+  if (tid == 0) {
+    p.acc[0] += lg;                                  // single CTA, launches are stream-ordered
+    if (*c.flag >= 0 && *p.flag < 0) *p.flag = *c.flag;
+  }
+}
+
+// ---- panel (mode 0: Cholesky panel of step j; mode 1: finalise block row j of the inverse)
+__global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j, int mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Shared sh;
+  cta_setup(sh, smem_raw, true);
+  Ctx& c = sh.c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
+  const int R0 = j * NB, ld = p.Tp;
+  float* M = mode ? p.Ut : p.W;
+  const int r_base = (mode ? 0 : R0 + NB) + CM * blockIdx.x;
+  const int row_end = mode ? R0 + NB : p.Tp;
+  const int gr = r_base + row;
+  stage_linv_from_dinv(c, p.dinv + (size_t)j * NB * NB);
+  float s[32], o[32];
+  if (gr < row_end) {
+    const float4* src = reinterpret_cast<const float4*>(M + (size_t)gr * ld + R0 + c0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = src[q];
+      s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s[q] = 0.f;
+  }
+  __syncthreads();
+  trsm_tc(c, s, o, row, half_id);
+  {
+    const int g0 = r_base + 32 * (warp & 3);
+    if (g0 < row_end) store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, M + (size_t)g0 * ld + R0 + c0, ld, lane);
+  }
+  float dot = 0.f, sq = 0.f;
+  if (gr < row_end) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      dot = fmaf(o[q], p.z[R0 + c0 + q], dot);
+      if (mode && gr < p.T && R0 + c0 + q < p.T) sq = fmaf(o[q], o[q], sq);
+    }
+  }
+  if (half_id) c.tmp[row] = dot;
+  __syncthreads();
+  if (half_id == 0 && gr < row_end) {
+    const float d2 = dot + c.tmp[row];
+    if (mode) p.alpha[gr] += d2;      // alpha = X^T z, one owner per row per launch
+    else p.z[gr] -= d2;               // right-looking forward substitution of the residual
+  }
+  if (mode) {
+    sq = block_sum(sq, c.red);
+    if (tid == 0) atomicAdd(p.acc + 1, sq);
+  }
+  cta_teardown(sh);
+}
+
+// ---- trailing update tiles (mode 0: W[i,c] -= W[i,j] W[c,j]^T;  mode 1: Ut[n,i] -= Ut[n,j] W[i,j]^T)
+__global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int j, int mode) {
+  const int R0 = j * NB, ld = p.Tp;
+  const int r_base = (mode ? 0 : R0 + NB) + CM * blockIdx.y;      // rows of the C tile
+  const int c_base = R0 + NB + NB * blockIdx.x;                    // columns of the C tile
+  const int row_end = mode ? R0 + NB : p.Tp;
+  if (r_base >= row_end || c_base >= p.Tp) return;
+  if (!mode && c_base > r_base + CM - 1) return;                   // tile entirely above the diagonal
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Shared sh;
+  cta_setup(sh, smem_raw, true);
+  Ctx& c = sh.c;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
+  float* Cm = mode ? p.Ut : p.W;
+  gemm_tc<false>(c, Cm, ld, r_base, row_end, c_base, R0, R0 + NB, nullptr, p.W);
+  float s[32];
+  tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, s);
+  tc_fence_before();
+  const int gr = r_base + row;
+  if (gr < row_end) {
+    float4* dst = reinterpret_cast<float4*>(Cm + (size_t)gr * ld + c_base + c0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 v = dst[q];
+      v.x -= s[4 * q]; v.y -= s[4 * q + 1]; v.z -= s[4 * q + 2]; v.w -= s[4 * q + 3];
+      dst[q] = v;
+    }
+  }
+  cta_teardown(sh);
+}
+
+// ---- scalars
+__global__ void __launch_bounds__(256) large_finish_kernel(LargeParams p, float jit_used, float* scalars, float* alpha_out, int* info) {
+  __shared__ float red[32];
+  float zz = 0.f, aa = 0.f, ar = 0.f;
+  for (int i = threadIdx.x; i < p.T; i += 256) {
+    const float zi = p.z[i], ai = p.alpha[i];
+    zz = fmaf(zi, zi, zz);
+    aa = fmaf(ai, ai, aa);
+    ar = fmaf(ai, p.resid[i], ar);
+    if (alpha_out) alpha_out[i] = ai;
+  }
+  const float inv_quad = block_sum(zz, red), alal = block_sum(aa, red), alr = block_sum(ar, red);
+  if (threadIdx.x == 0) {
+    const float Tf = (float)p.T, logdet = 2.f * p.acc[0], tr = p.acc[1];
+    scalars[0] = -0.5f * (inv_quad + logdet + Tf * 1.8378770664093453f) / Tf;
+    scalars[1] = 0.5f * (alal - tr) / Tf;
+    scalars[2] = logdet; scalars[3] = inv_quad; scalars[4] = tr; scalars[5] = alal; scalars[6] = alr; scalars[7] = jit_used;
+    for (int q = 8; q < NSCALARS; ++q) scalars[q] = 0.f;
+    if (info) *info = (*p.flag >= 0) ? *p.flag + 1 : 0;
+  }
+}
+
+}  // namespace large
+
+// One series per call (the dispatcher loops over the batch).  Returns VOLT_OK; numerical failure is reported in info.
+int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
+  using namespace large;
+  LargeParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = mp.T;
+  p.Tp = (mp.T + NB - 1) / NB * NB;
+  p.nb = p.Tp / NB;
+  p.kind = mp.kind;
+  const size_t tp2 = (size_t)p.Tp * p.Tp;
+  void *w = nullptr, *u = nullptr, *aux = nullptr;
+  int s = get_workspace(tp2 * sizeof(float), &w, 9);
+  if (s) return s;
+  s = get_workspace(tp2 * sizeof(float), &u, 10);
+  if (s) return s;
+  const size_t aux_fl = (size_t)p.nb * NB * NB + 2 * (size_t)p.Tp + 16;
+  s = get_workspace(aux_fl * sizeof(float), &aux, 11);
+  if (s) return s;
+  p.W = (float*)w;
+  p.Ut = (float*)u;
+  p.dinv = (float*)aux;
+  p.z = p.dinv + (size_t)p.nb * NB * NB;
+  p.alpha = p.z + p.Tp;
+  p.acc = p.alpha + p.Tp;
+  p.flag = reinterpret_cast<int*>(p.acc + 4);
+  if (mp.kind == KIND_VOL) p.V = mp.V + (size_t)b * mp.T;
+  else if (mp.kind == KIND_BM) { p.V = mp.x; }
+  else { p.dense = mp.dense + (size_t)b * mp.dense_bstride; p.ldd = mp.ldd; }
+  p.resid = mp.resid + (size_t)b * mp.T;
+  float scale = 1.f, dadd0 = 0.f;
+  if (mp.kind == KIND_BM) VOLT_CUDA(cudaMemcpyAsync(&scale, mp.scale + (size_t)b * mp.scale_stride, 4, cudaMemcpyDeviceToHost, st));
+  if (mp.diag_add) VOLT_CUDA(cudaMemcpyAsync(&dadd0, mp.diag_add + (size_t)b * mp.diag_stride, 4, cudaMemcpyDeviceToHost, st));
+  if (mp.kind == KIND_BM || mp.diag_add) VOLT_CUDA(cudaStreamSynchronize(st));
+  p.scale = scale;
+  static bool attr = false;
+  if (!attr) {
+    VOLT_CUDA(cudaFuncSetAttribute(large_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
+    VOLT_CUDA(cudaFuncSetAttribute(large_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
+    VOLT_CUDA(cudaFuncSetAttribute(large_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
+    attr = true;
+  }
+  float jit_used = 0.f;
+  for (int attempt = 0;; ++attempt) {
+    p.dadd = dadd0 + jit_used;
+    VOLT_CUDA(cudaMemsetAsync(p.Ut, 0, tp2 * sizeof(float), st));
+    large_build_kernel<<<p.Tp, 256, 0, st>>>(p);
+    for (int j = 0; j < p.nb; ++j) {
+      large_diag_kernel<<<1, NT, LARGE_SMEM, st>>>(p, j);
+      const int rows = p.Tp - (j + 1) * NB;
+      if (rows > 0) {
+        large_panel_kernel<<<(rows + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, j, 0);
+        dim3 grid(rows / NB, (rows + CM - 1) / CM);
+        large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, j, 0);
+      }
+    }
+    int flag = -1;
+    VOLT_CUDA(cudaMemcpyAsync(&flag, p.flag, 4, cudaMemcpyDeviceToHost, st));
+    VOLT_CUDA(cudaStreamSynchronize(st));
+    if (flag < 0 || attempt >= mp.max_tries || !(mp.jitter > 0.f)) break;
+    jit_used = mp.jitter * powf(10.f, (float)attempt);
+  }
+  if (mp.do_inverse) {
+    for (int k = 0; k < p.nb; ++k) {
+      const int rows_done = (k + 1) * NB;
+      large_panel_kernel<<<(rows_done + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, k, 1);
+      const int cols = p.Tp - rows_done;
+      if (cols > 0) {
+        dim3 grid(cols / NB, (rows_done + CM - 1) / CM);
+        large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, k, 1);
+      }
+    }
+  }
+  large_finish_kernel<<<1, 256, 0, st>>>(p, jit_used, mp.scalars + (size_t)b * NSCALARS,
+                                         (mp.alpha && mp.do_inverse) ? mp.alpha + (size_t)b * mp.T : nullptr,
+                                         mp.info ? mp.info + b : nullptr);
+  return check_cuda(cudaGetLastError(), "mll_large_kernels");
+}
+
+}  // namespace volt

@@ -15,256 +15,10 @@
 //             U[0:i, i] = -G^T Linv_ii^T                            K = 64
 // SIMT work that remains: the 64x64 diagonal potrf / trtri (chol_dev.cuh), the hi/lo split while staging operand
 // tiles, the forward substitution for z, and the reductions.
-#include "chol_dev.cuh"
+#include "chol_tc_dev.cuh"
 
 namespace volt {
 namespace tc {
-
-constexpr int CLD = NB + 4;                   // Ct / LiT row stride (floats)
-constexpr uint32_t A_TILE = 128u * 128u;      // bytes of one 128-row x 32-float operand tile
-constexpr uint32_t B_TILE = 64u * 128u;       // bytes of one 64-row x 32-float operand tile
-// shared-memory map (byte offsets from a 1024-aligned base)
-constexpr uint32_t X_AHI = 0, X_ALO = A_TILE, X_BHI = 2 * A_TILE, X_BLO = 2 * A_TILE + B_TILE;
-constexpr uint32_t X_BYTES = 2 * A_TILE + 2 * B_TILE;           // 48 KB GEMM stage; aliased by P (hi|lo) and LiT|tmp
-constexpr uint32_t X_LIT = 0, X_TMP = 64 * CLD * 4;             // LiT 17408 B, diag scratch 14336 B,
-constexpr uint32_t X_STASH = 32768;                             // 16 KB stash of the chunk-0 panel rows  (<= 48 KB)
-constexpr uint32_t L_OFF = X_BYTES;                             // Linv operand: hi k-tile0, hi k-tile1, lo k-tile0, lo k-tile1
-constexpr uint32_t L_BYTES = 4 * B_TILE;                        // 32 KB
-constexpr uint32_t CT_OFF = L_OFF + L_BYTES;                    // diagonal block D, row-major, stride CLD
-constexpr uint32_t CT_BYTES = 64 * CLD * 4;
-constexpr uint32_t VEC_OFF = CT_OFF + CT_BYTES;
-
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, SWIZZLE_128B operand descriptor: 8-row groups are 1024 B apart (SBO), LBO unused, version 1 (sm_100).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024u >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra D_%=;\n\t"
-      "bra W_%=;\n\t"
-      "D_%=:\n\t}" ::"r"(s_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 32 consecutive accumulator columns of this thread's TMEM lane (warp w reads lanes 32 (w%4) .. +31)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// store one 16-byte chunk (4 consecutive k) of row `row` into a hi and a lo K-major SW128 tile
-__device__ __forceinline__ void st_split(uint8_t* hi_tile, uint8_t* lo_tile, int row, int chunk, float4 v) {
-  const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-  float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
-}
-
-struct Ctx {
-  uint8_t* X;        // 48 KB stage / alias region
-  uint8_t* Lr;       // 32 KB Linv operand (hi0, hi1, lo0, lo1)
-  float* Ct;
-  float* Vs; float* z; float* al; float* z2;
-  float* diagl; float* tmp; float* red; int* flag;
-  uint64_t* bar;
-  uint32_t tmem;     // TMEM base (128 columns: acc0 = [0,64), acc1 = [64,128))
-  uint32_t phase;    // parity of the next mbarrier completion to wait for
-};
-
-__device__ __forceinline__ void wait_mma(Ctx& c) {
-  mbar_wait(c.bar, c.phase);
-  c.phase ^= 1u;
-}
-
-// 3xTF32 product of one k-tile (32 floats): D (+)= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T.  One thread issues.
-__device__ __forceinline__ void issue_ktile(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, bool first) {
-  const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const uint64_t adv = (uint64_t)(2 * ks);  // 32 bytes per K=8 step, in 16-byte units
-    umma_tf32(tmem_d, dal + adv, dbh + adv, (first && ks == 0) ? 0u : 1u);
-    umma_tf32(tmem_d, dah + adv, dbl + adv, 1u);
-    umma_tf32(tmem_d, dah + adv, dbh + adv, 1u);
-  }
-}
-
-// acc0 = A[a_row0 + r, k_lo:k_hi] . Bm[b_row0 + n, k_lo:k_hi]^T  on the tensor cores (r < 128, n < 64).
-// Returns false when the k-range is empty (acc0 untouched).
-template <bool PHASE_B>
-__device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_end, int b_row0, int k_lo, int k_hi, const float* dinv) {
-  const int tid = threadIdx.x;
-  const int nk = (k_hi - k_lo) / 32;
-  if (nk <= 0) return false;
-  float4 ra[4], rb[2];
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + NT * i, row = idx >> 3, chunk = idx & 7;
-      ra[i] = load_a<PHASE_B>(S, ld, a_row0 + row, a_row_end, k0 + chunk * 4, dinv);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + NT * i, row = idx >> 3, chunk = idx & 7;
-      rb[i] = *reinterpret_cast<const float4*>(S + (size_t)(b_row0 + row) * ld + k0 + chunk * 4);
-    }
-  };
-  gload(k_lo);
-  for (int kt = 0; kt < nk; ++kt) {
-    if (kt > 0) wait_mma(c);  // the previous k-tile's MMAs have consumed the stage
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + NT * i;
-      st_split(c.X + X_AHI, c.X + X_ALO, idx >> 3, idx & 7, ra[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + NT * i;
-      st_split(c.X + X_BHI, c.X + X_BLO, idx >> 3, idx & 7, rb[i]);
-    }
-    if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t xb = s_u32(c.X);
-      issue_ktile(c.tmem, xb + X_AHI, xb + X_ALO, xb + X_BHI, xb + X_BLO, kt == 0);
-      umma_commit(c.bar);
-    }
-  }
-  wait_mma(c);
-  tc_fence_after();
-  return true;
-}
-
-// out = P . Linv^T where P (128 x 64, one row per (thread, column half)) is in registers `s`, Linv hi/lo already in c.Lr.
-// Two K halves (the warps holding columns 0..31 stage first, then the warps holding 32..63); result in acc1 -> `o`.
-__device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int row, int half_id) {
-  const int tid = threadIdx.x;
-  const uint32_t xb = s_u32(c.X), lb = s_u32(c.Lr);
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (half_id == half) {
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        st_split(c.X, c.X + A_TILE, row, ch, make_float4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]));
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_ktile(c.tmem + 64, xb, xb + A_TILE, lb + half * B_TILE, lb + (2 + half) * B_TILE, half == 0);
-      umma_commit(c.bar);
-    }
-    wait_mma(c);
-  }
-  tc_fence_after();
-  const int w = tid >> 5;
-  tmem_ld32(c.tmem + ((uint32_t)(32 * (w & 3)) << 16) + 64u + (uint32_t)(half_id * 32), o);
-  tc_fence_before();
-}
-
-// Linv operand (B of the TRSM product): B[n][k] = Linv[n][k] = LiT[k][n], LiT with row stride CLD (floats).
-__device__ __forceinline__ void stage_linv_from_lit(Ctx& c, const float* LiT) {
-  for (int q = threadIdx.x; q < 64 * 16; q += NT) {
-    const int n = q >> 4, kc = q & 15;  // kc: 16-byte chunk over k = 0..63
-    const int k = kc * 4;
-    const float4 v = make_float4(LiT[(k + 0) * CLD + n], LiT[(k + 1) * CLD + n], LiT[(k + 2) * CLD + n], LiT[(k + 3) * CLD + n]);
-    const int kt = kc >> 3;
-    st_split(c.Lr + kt * B_TILE, c.Lr + (2 + kt) * B_TILE, n, kc & 7, v);
-  }
-}
-// same from the global Dinv block (Dinv[m][k'] = Linv[k'][m]  ->  Linv[n][k] = Dinv[k][n])
-__device__ __forceinline__ void stage_linv_from_dinv(Ctx& c, const float* D) {
-  for (int q = threadIdx.x; q < 64 * 16; q += NT) {
-    const int n = q & 63, kc = q >> 6;
-    const int k = kc * 4;
-    const float4 v = make_float4(D[(k + 0) * NB + n], D[(k + 1) * NB + n], D[(k + 2) * NB + n], D[(k + 3) * NB + n]);
-    const int kt = kc >> 3;
-    st_split(c.Lr + kt * B_TILE, c.Lr + (2 + kt) * B_TILE, n, kc & 7, v);
-  }
-}
-
-// A-generator for one accumulator row: s[q] <- A[gr][gc0 + q] - s[q], q = 0..31.  Fast path (no identity padding, on-the-fly
-// kernels): the 32 column values come from 8 broadcast LDS.128 of the staged prefix vector.
-__device__ __forceinline__ void gen_sub_row32(const MllParams& p, int b, int gr, int gc0, const float* Vs, float sc, float dadd,
-                                              float (&s)[32]) {
-  if (p.kind != KIND_DENSE && p.T == p.Tp) {
-    const float vr = Vs[gr];
-    const bool vol = (p.kind == KIND_VOL);
-#pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
-      const float4 cv = *reinterpret_cast<const float4*>(Vs + gc0 + 4 * q4);
-      const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int gc = gc0 + 4 * q4 + e;
-        float v = vol ? ((gc <= gr) ? c4[e] : vr) : sc * fminf(vr, c4[e]);
-        if (gc == gr) v += dadd;
-        s[4 * q4 + e] = v - s[4 * q4 + e];
-      }
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 32; ++q) s[q] = gen_entry(p, b, gr, gc0 + q, Vs, sc, dadd) - s[q];
-  }
-}
-
-// Coalesced store of a warp's 32 x 32 block (lane = row, 32 columns in registers): transposed through a private
-// 32 x 36 float shared-memory tile so that every STG.128 writes 4 full 128-byte rows instead of 32 row fragments.
-__device__ __forceinline__ void store_block32(float* xs, const float (&o)[32], float* gdst /* row 0, col 0 of the block */, int ld,
-                                              int lane) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(xs + lane * 36 + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = (lane >> 3) + 4 * i, ch = (lane & 7) * 4;
-    *reinterpret_cast<float4*>(gdst + (size_t)r * ld + ch) = *reinterpret_cast<const float4*>(xs + r * 36 + ch);
-  }
-}
 
 __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
