@@ -192,14 +192,18 @@ __global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j
   cta_teardown(sh);
 }
 
-// ---- trailing update tiles (mode 0: W[i,c] -= W[i,j] W[c,j]^T;  mode 1: Ut[n,i] -= Ut[n,j] W[i,j]^T)
-__global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int j, int mode) {
-  const int R0 = j * NB, ld = p.Tp;
-  const int r_base = (mode ? 0 : R0 + NB) + CM * blockIdx.y;      // rows of the C tile
-  const int c_base = R0 + NB + NB * blockIdx.x;                    // columns of the C tile
-  const int row_end = mode ? R0 + NB : p.Tp;
-  if (r_base >= row_end || c_base >= p.Tp) return;
-  if (!mode && c_base > r_base + CM - 1) return;                   // tile entirely above the diagonal
+// ---- trailing update tiles: C[rows, cols] -= A[rows, k_lo:k_hi] B[cols, k_lo:k_hi]^T, 128 x 64 tiles.
+//   mode 0 (Cholesky):  A = C = W, B = W; rows >= row_lo, only tiles touching the lower triangle.
+//   mode 1 (inverse):   A = C = Ut, B = W; rows < row_end (Ut is upper triangular).
+// The host calls it with K = 64 inside a 256-column panel and once with K = 256 for everything to the right of the
+// panel, which cuts the read-modify-write traffic on C by 4x compared with a plain NB = 64 right-looking sweep.
+__global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int mode, int row_lo, int row_end, int col_lo, int col_hi,
+                                                             int k_lo, int k_hi) {
+  const int ld = p.Tp;
+  const int r_base = row_lo + CM * blockIdx.y;      // rows of the C tile
+  const int c_base = col_lo + NB * blockIdx.x;      // columns of the C tile
+  if (r_base >= row_end || c_base >= col_hi) return;
+  if (!mode && c_base > r_base + CM - 1) return;    // tile entirely above the diagonal
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Shared sh;
   cta_setup(sh, smem_raw, true);
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
   float* Cm = mode ? p.Ut : p.W;
-  gemm_tc<false>(c, Cm, ld, r_base, row_end, c_base, R0, R0 + NB, nullptr, p.W);
+  gemm_tc<false>(c, Cm, ld, r_base, row_end, c_base, k_lo, k_hi, nullptr, p.W);
   float s[32];
   tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, s);
   tc_fence_before();
@@ -294,13 +298,21 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     p.dadd = dadd0 + jit_used;
     VOLT_CUDA(cudaMemsetAsync(p.Ut, 0, tp2 * sizeof(float), st));
     large_build_kernel<<<p.Tp, 256, 0, st>>>(p);
+    constexpr int PB = 4;  // blocks per panel: trailing updates outside the panel are deferred and applied with K = 256
+    auto update = [&](int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
+      const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
+      if (nrow <= 0 || ncol <= 0) return;
+      dim3 grid(ncol, nrow);
+      large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
+    };
     for (int j = 0; j < p.nb; ++j) {
+      const int R0 = j * NB, panel_end = min(p.Tp, (j / PB + 1) * PB * NB);
       large_diag_kernel<<<1, NT, LARGE_SMEM, st>>>(p, j);
-      const int rows = p.Tp - (j + 1) * NB;
+      const int rows = p.Tp - (R0 + NB);
       if (rows > 0) {
         large_panel_kernel<<<(rows + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, j, 0);
-        dim3 grid(rows / NB, (rows + CM - 1) / CM);
-        large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, j, 0);
+        update(0, R0 + NB, p.Tp, R0 + NB, panel_end, R0, R0 + NB);                  // inside the panel, K = 64
+        if (R0 + NB == panel_end) update(0, panel_end, p.Tp, panel_end, p.Tp, panel_end - PB * NB, panel_end);  // K = 256
       }
     }
     int flag = -1;
@@ -310,14 +322,18 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     jit_used = mp.jitter * powf(10.f, (float)attempt);
   }
   if (mp.do_inverse) {
+    constexpr int PB = 4;
+    auto update = [&](int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
+      const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
+      if (nrow <= 0 || ncol <= 0) return;
+      dim3 grid(ncol, nrow);
+      large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
+    };
     for (int k = 0; k < p.nb; ++k) {
-      const int rows_done = (k + 1) * NB;
+      const int R0 = k * NB, rows_done = R0 + NB, panel_end = min(p.Tp, (k / PB + 1) * PB * NB);
       large_panel_kernel<<<(rows_done + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, k, 1);
-      const int cols = p.Tp - rows_done;
-      if (cols > 0) {
-        dim3 grid(cols / NB, (rows_done + CM - 1) / CM);
-        large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, k, 1);
-      }
+      update(1, 0, rows_done, rows_done, panel_end, R0, rows_done);                 // columns inside the panel, K = 64
+      if (rows_done == panel_end) update(1, 0, panel_end, panel_end, p.Tp, panel_end - PB * NB, panel_end);  // K = 256
     }
   }
   large_finish_kernel<<<1, 256, 0, st>>>(p, jit_used, mp.scalars + (size_t)b * NSCALARS,
