@@ -198,17 +198,24 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
       for (int i = 0; i < nb; ++i) {
         const int R0 = i * NB;
         const float* Di = dinv + (size_t)i * NB * NB;
-        stage_linv_from_dinv(c, Di);
+        // bring the inverted diagonal block back into shared memory once (coalesced), then stage the TRSM operand and
+        // take its own contribution to tr(A^-1) and alpha from there
+        for (int idx = tid; idx < NB * NB / 4; idx += NT) {
+          const int r = idx >> 4, c4 = (idx & 15) * 4;
+          *reinterpret_cast<float4*>(LiT + r * CLD + c4) = *reinterpret_cast<const float4*>(Di + r * NB + c4);
+        }
+        __syncthreads();
+        stage_linv_from_lit(c, LiT);
         for (int idx = tid; idx < NB * NB; idx += NT) {
           const int m = idx >> 6, cc = idx & 63;
           if (R0 + m < T && R0 + cc < T) {
-            const float v = Di[idx];
+            const float v = LiT[m * CLD + cc];
             tr_part = fmaf(v, v, tr_part);
           }
         }
         if (tid < NB) {
           float a = 0.f;
-          for (int cc = tid; cc < NB; ++cc) a = fmaf(Di[tid * NB + cc], c.z[R0 + cc], a);
+          for (int cc = tid; cc < NB; ++cc) a = fmaf(LiT[tid * CLD + cc], c.z[R0 + cc], a);
           c.al[R0 + tid] += a;
         }
         __syncthreads();
