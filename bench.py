@@ -253,6 +253,13 @@ def main():
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
 
     pk = peaks()
+    traffic = None  # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, committed)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f).get(args.workload)
+        if tj:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     # algorithmic work per eval: bytes 4 T^2 + 12 T (build fused into the factorisation),
     # flops 2 T^3 / 3 (potrf + trtri) + 4 T^2
     bytes_per_eval = 4.0 * T * T + 12.0 * T
@@ -269,7 +276,7 @@ def main():
                  d2h_bytes_per_step=int(B * 16 * 4 + B * 4)),
         gpu_launches=int(launches),
         clocks=clocks,
-        roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=None,
+        roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=traffic,
                       kernel="mll_batched_tc_kernel (+ cumtrapz_kernel, <1% of the time)", ms_per_launch=kern_ms, bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
         roofline_tensor=dict(bound="tensor", achieved=ach_tf, peak=pk["tf"], unit="TFLOP/s", frac=ach_tf / pk["tf"],
                              flops_per_eval=flops_per_eval, note="tcgen05 kind::tf32 3-pass split (hi*hi + hi*lo + lo*hi): 3x the algorithmic flops are issued on the tensor pipe; peak is the measured bf16 dense GEMM figure (nominal TF32 peak is half of bf16)"),
