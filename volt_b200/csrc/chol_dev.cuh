@@ -147,311 +147,12 @@ __device__ void trtri64(const float* Ct, float* LiT, float* tmpbuf) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------- warp-level diagonal block
-// One warp factors and inverts the 64x64 diagonal block as a 2x2 grid of 32x32 blocks, one matrix row (or inverse
-// column) per lane held in registers, operands broadcast through small shared-memory panels (no block barriers):
-//   L11 = chol(S11); L21 = S21 L11^-T; S22 -= L21 L21^T; L22 = chol(S22);
-//   Li11 = L11^-1, Li22 = L22^-1 (one column per lane, forward substitution); Li21 = -Li22 (L21 Li11).
-// In/out: Ct (column-major, stride CLD; lower triangle valid on entry, L on exit), LiT[k][c] = Linv[c][k],
-// diagl[r] = L[r][r]; tmp: >= 3*32*DW_LD + 128 floats of scratch.  All 32 lanes of the calling warp must be active.
-constexpr int DW_LD = 36;  // row stride of the 32x32 broadcast panels (floats, 16-byte aligned rows)
-
-#define VOLT_CBAR() asm volatile("" ::: "memory")
-
-// sum_{t < N} row[t] * x[t] with four independent accumulators; `row` is a 16-byte aligned shared-memory row that
-// every lane reads at the same address (broadcast).  N is a compile-time constant after unrolling.
-template <int N>
-__device__ __forceinline__ float dot_bcast(const float* row, const float (&x)[32]) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int t = 0; t < N; t += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + t);
-    s0 = fmaf(v.x, x[t], s0);
-    if (t + 1 < N) s1 = fmaf(v.y, x[t + 1], s1);
-    if (t + 2 < N) s2 = fmaf(v.z, x[t + 2], s2);
-    if (t + 3 < N) s3 = fmaf(v.w, x[t + 3], s3);
-  }
-  return (s0 + s1) + (s2 + s3);
-}
-
-// right-looking Cholesky of a 32x32 block, lane = row, a[k] = S[lane][k] (k <= lane valid).  colbuf: 64 floats.
-__device__ __forceinline__ void potrf32_warp(float (&a)[32], float* colbuf, int lane, int& failc, int off) {
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const float d = __shfl_sync(0xffffffffu, a[c], c);
-    if (!(d > 0.f) && failc < 0) failc = off + c;
-    const float l = sqrtf(d);
-    const float inv = 1.f / l;
-    const float lrc = (lane == c) ? l : a[c] * inv;
-    a[c] = lrc;
-    float* cb = colbuf + (c & 1) * 32;
-    cb[lane] = lrc;
-    __syncwarp();
-#pragma unroll
-    for (int k4 = (c + 1) & ~3; k4 < 32; k4 += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(cb + k4);
-      if (k4 > c) a[k4] = fmaf(-lrc, v.x, a[k4]);
-      if (k4 + 1 > c) a[k4 + 1] = fmaf(-lrc, v.y, a[k4 + 1]);
-      if (k4 + 2 > c) a[k4 + 2] = fmaf(-lrc, v.z, a[k4 + 2]);
-      if (k4 + 3 > c) a[k4 + 3] = fmaf(-lrc, v.w, a[k4 + 3]);
-    }
-    VOLT_CBAR();
-  }
-}
-
-// forward substitution with the row-major lower-triangular panel Lp (stride DW_LD) and reciprocal diagonal invd:
-// x <- solution of (x' L^T = x) when UNIT_RHS == false (x holds the right-hand side), or column `lane` of L^-1 when
-// UNIT_RHS == true (x is overwritten).
-template <bool UNIT_RHS, int K>
-struct FwdSub {
-  static __device__ __forceinline__ void run(float (&x)[32], const float* Lp, const float* invd, int lane) {
-    FwdSub<UNIT_RHS, K - 1>::run(x, Lp, invd, lane);
-    constexpr int k = K - 1;
-    const float rhs = UNIT_RHS ? ((k == lane) ? 1.f : 0.f) : x[k];
-    const float acc = rhs - dot_bcast<k>(Lp + k * DW_LD, x);
-    x[k] = acc * invd[k];
-    VOLT_CBAR();
-  }
-};
-template <bool UNIT_RHS>
-struct FwdSub<UNIT_RHS, 0> {
-  static __device__ __forceinline__ void run(float (&)[32], const float*, const float*, int) {}
-};
-
-// y[r] = sum_{t < (TRI ? r+1 : 32)} P[r][t] * x[t] for r = 0..31 (P row-major, stride DW_LD, broadcast reads)
-template <bool TRI, int R>
-struct MatVec {
-  static __device__ __forceinline__ void run(float (&y)[32], const float* P, const float (&x)[32]) {
-    MatVec<TRI, R - 1>::run(y, P, x);
-    constexpr int r = R - 1;
-    y[r] = dot_bcast<(TRI ? r + 1 : 32)>(P + r * DW_LD, x);
-    VOLT_CBAR();
-  }
-};
-template <bool TRI>
-struct MatVec<TRI, 0> {
-  static __device__ __forceinline__ void run(float (&)[32], const float*, const float (&)[32]) {}
-};
-
-template <int CLD>
-__device__ void diag64_warp(float* Ct, float* LiT, float* tmp, float* diagl, int* flag, int col0) {
-  const int lane = threadIdx.x & 31;
-  float* P0 = tmp;                    // L11 (row-major), later L22
-  float* P1 = tmp + 32 * DW_LD;       // L21
-  float* P2 = tmp + 64 * DW_LD;       // Li22 (row-major)
-  float* colbuf = tmp + 96 * DW_LD;   // 64 floats
-  float* invd = colbuf + 64;          // 64 floats: 1 / L[r][r]
-  int failc = -1;
-  float a[32], x[32];
-
-  // ---- L11 = chol(S11)   (lane = row)
-#pragma unroll
-  for (int k = 0; k < 32; ++k) a[k] = Ct[k * CLD + lane];
-  potrf32_warp(a, colbuf, lane, failc, 0);
-  {
-    float dl = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float v = (k <= lane) ? a[k] : 0.f;
-      dl = (k == lane) ? v : dl;
-      P0[lane * DW_LD + k] = v;
-      Ct[k * CLD + lane] = v;
-    }
-    diagl[lane] = dl;
-    invd[lane] = 1.f / dl;
-  }
-  __syncwarp();
-  // ---- L21 = S21 L11^-T  (lane = row 32 + lane)
-#pragma unroll
-  for (int k = 0; k < 32; ++k) x[k] = Ct[k * CLD + 32 + lane];
-  FwdSub<false, 32>::run(x, P0, invd, lane);
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    P1[lane * DW_LD + k] = x[k];
-    Ct[k * CLD + 32 + lane] = x[k];
-  }
-  // ---- Li11 (lane = column m): a[k] = Linv11[k][m]
-  FwdSub<true, 32>::run(a, P0, invd, lane);
-#pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    *reinterpret_cast<float4*>(LiT + lane * CLD + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
-    *reinterpret_cast<float4*>(LiT + (32 + lane) * CLD + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncwarp();
-  // ---- S22 -= L21 L21^T ; L22 = chol(S22)   (lane = row 32 + lane; x = its L21 row)
-  MatVec<false, 32>::run(a, P1, x);
-#pragma unroll
-  for (int k = 0; k < 32; ++k) a[k] = Ct[(32 + k) * CLD + 32 + lane] - a[k];
-  potrf32_warp(a, colbuf, lane, failc, 32);
-  __syncwarp();
-  {
-    float dl = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float v = (k <= lane) ? a[k] : 0.f;
-      dl = (k == lane) ? v : dl;
-      P0[lane * DW_LD + k] = v;
-      Ct[(32 + k) * CLD + 32 + lane] = v;
-    }
-    diagl[32 + lane] = dl;
-    invd[32 + lane] = 1.f / dl;
-  }
-  __syncwarp();
-  // ---- Li22 (lane = column m)
-  FwdSub<true, 32>::run(a, P0, invd + 32, lane);
-#pragma unroll
-  for (int k = 0; k < 32; ++k) P2[k * DW_LD + lane] = a[k];
-#pragma unroll
-  for (int k = 0; k < 32; k += 4)
-    *reinterpret_cast<float4*>(LiT + (32 + lane) * CLD + 32 + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
-  __syncwarp();
-  // ---- Li21 = -Li22 (L21 Li11)   (lane = column m): x = Li11[:, m]; a = L21 x; x = Li22 a
-#pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(LiT + lane * CLD + k);
-    x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
-  }
-  MatVec<false, 32>::run(a, P1, x);
-  MatVec<true, 32>::run(x, P2, a);
-#pragma unroll
-  for (int k = 0; k < 32; k += 4)
-    *reinterpret_cast<float4*>(LiT + lane * CLD + 32 + k) = make_float4(-x[k], -x[k + 1], -x[k + 2], -x[k + 3]);
-  if (lane == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
-  __syncwarp();
-}
-
-// ---------------------------------------------------------------------------------------------- compact diagonal block
-// Block-cooperative factor + inverse of the 64x64 diagonal block with ROLLED loops (small code: the fully unrolled
-// warp version above is instruction-fetch bound) as a 2x2 grid of 32x32 blocks:
-//   warp 0: L11 = chol(S11) | warp 0: L21 = S21 L11^-T, warp 1: Li11 | all: S22 -= L21 L21^T |
-//   warp 0: L22 = chol(S22), warps 1-7: W^T = Li11^T-rows . L21-rows | warp 0: Li22 | all: Li21 = -Li22 W.
-// D: row-major diagonal block, stride RLD (lower triangle valid on entry; L with a zeroed strict upper triangle in
-// each 32x32 diagonal sub-block on exit).  LiT[k][c] = Linv[c][k] (stride RLD).  scratch: >= 2*32*36 + 32 + 64 floats.
-// Must be called by all threads of the CTA (contains __syncthreads).
-template <int RLD>
-__device__ __forceinline__ void potrf32_rolled(float* D, int o, float* colbuf, float* invd, float* diagl, int lane, int& failc) {
-  float* rowp = D + (o + lane) * RLD + o;
-  for (int c = 0; c < 32; ++c) {
-    const float d = D[(o + c) * RLD + o + c];
-    if (!(d > 0.f) && failc < 0) failc = o + c;
-    const float l = sqrtf(d);
-    const float inv = 1.f / l;
-    const float lrc = (lane == c) ? l : rowp[c] * inv;
-    if (lane >= c) rowp[c] = lrc; else rowp[c] = 0.f;
-    colbuf[lane] = lrc;
-    if (lane == c) { diagl[o + c] = l; invd[o + c] = inv; }
-    __syncwarp();
-    for (int k4 = (c + 1) & ~3; k4 < 32; k4 += 4) {
-      const float4 cb = *reinterpret_cast<const float4*>(colbuf + k4);
-      float4 own = *reinterpret_cast<float4*>(rowp + k4);
-      if (k4 > c) own.x = fmaf(-lrc, cb.x, own.x);
-      if (k4 + 1 > c) own.y = fmaf(-lrc, cb.y, own.y);
-      if (k4 + 2 > c) own.z = fmaf(-lrc, cb.z, own.z);
-      own.w = fmaf(-lrc, cb.w, own.w);
-      *reinterpret_cast<float4*>(rowp + k4) = own;
-    }
-    __syncwarp();
-  }
-}
-
-// x[k] <- (rhs_k - sum_{t<k} L[k][t] x[t]) * invd[k], k = 0..31; L row-major (stride RLD, zero above the diagonal),
-// x a private row per lane.  unit: rhs = e_lane (x must be zero-initialised), otherwise rhs = x[k] on entry.
-template <int RLD>
-__device__ __forceinline__ void fwdsub32_rolled(const float* L, float* x, const float* invd, bool unit, int lane) {
-  for (int k = 0; k < 32; ++k) {
-    const float* Lk = L + k * RLD;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int t4 = 0; t4 < k; t4 += 4) {
-      const float4 l4 = *reinterpret_cast<const float4*>(Lk + t4);
-      const float4 x4 = *reinterpret_cast<const float4*>(x + t4);
-      a0 = fmaf(l4.x, x4.x, a0);
-      if (t4 + 1 < k) a1 = fmaf(l4.y, x4.y, a1);
-      if (t4 + 2 < k) a2 = fmaf(l4.z, x4.z, a2);
-      if (t4 + 3 < k) a3 = fmaf(l4.w, x4.w, a3);
-    }
-    const float rhs = unit ? ((k == lane) ? 1.f : 0.f) : x[k];
-    x[k] = (rhs - ((a0 + a1) + (a2 + a3))) * invd[k];
-  }
-}
-
-__device__ __forceinline__ float dot32(const float* a, const float* b) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int t = 0; t < 32; t += 4) {
-    const float4 u = *reinterpret_cast<const float4*>(a + t);
-    const float4 v = *reinterpret_cast<const float4*>(b + t);
-    s0 = fmaf(u.x, v.x, s0); s1 = fmaf(u.y, v.y, s1); s2 = fmaf(u.z, v.z, s2); s3 = fmaf(u.w, v.w, s3);
-  }
-  return (s0 + s1) + (s2 + s3);
-}
-
-constexpr int DIAG_SCRATCH_FLOATS = 2 * 32 * 36 + 32 + 64;
-
-template <int RLD>
-__device__ void diag64_block(float* D, float* LiT, float* scratch, float* diagl, int* flag, int col0) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* Li22r = scratch;              // 32 x 36 row-major Li22
-  float* WT = scratch + 32 * 36;       // 32 x 36: WT[m][r] = (L21 Li11)[r][m]
-  float* colbuf = WT + 32 * 36;        // 32
-  float* invd = colbuf + 32;           // 64
-  int failc = -1;
-  // ---- S0: L11
-  if (warp == 0) potrf32_rolled<RLD>(D, 0, colbuf, invd, diagl, lane, failc);
-  else {
-    for (int i = tid - 32; i < 64 * 64; i += NT - 32) LiT[(i >> 6) * RLD + (i & 63)] = 0.f;
-    for (int i = tid - 32; i < 32 * 36; i += NT - 32) Li22r[i] = 0.f;
-  }
-  __syncthreads();
-  // ---- S1: L21 (warp 0)  ||  Li11 (warp 1)
-  if (warp == 0) fwdsub32_rolled<RLD>(D, D + (32 + lane) * RLD, invd, false, lane);
-  else if (warp == 1) fwdsub32_rolled<RLD>(D, LiT + lane * RLD, invd, true, lane);
-  __syncthreads();
-  // ---- S2: S22 -= L21 L21^T (lower part only)
-  {
-    const int r = tid >> 3, k0 = (tid & 7) * 4;
-    if (k0 <= r) {
-      const float* xr = D + (32 + r) * RLD;
-      float* out = D + (32 + r) * RLD + 32 + k0;
-      float4 o4 = *reinterpret_cast<float4*>(out);
-      o4.x -= dot32(xr, D + (32 + k0) * RLD);
-      o4.y -= dot32(xr, D + (33 + k0) * RLD);
-      o4.z -= dot32(xr, D + (34 + k0) * RLD);
-      o4.w -= dot32(xr, D + (35 + k0) * RLD);
-      *reinterpret_cast<float4*>(out) = o4;
-    }
-  }
-  __syncthreads();
-  // ---- S3: L22 (warp 0)  ||  WT (warps 1..7)
-  if (warp == 0) potrf32_rolled<RLD>(D, 32, colbuf, invd, diagl, lane, failc);
-  else {
-    for (int i = tid - 32; i < 32 * 32; i += NT - 32) {
-      const int m = i >> 5, r = i & 31;
-      WT[m * 36 + r] = dot32(LiT + m * RLD, D + (32 + r) * RLD);
-    }
-  }
-  __syncthreads();
-  // ---- S4: Li22 (warp 0): column `lane` -> LiT row 32+lane (cols 32..63) and the row-major copy Li22r
-  if (warp == 0) {
-    float* y = LiT + (32 + lane) * RLD + 32;
-    fwdsub32_rolled<RLD>(D + 32 * RLD + 32, y, invd + 32, true, lane);
-    for (int k = 0; k < 32; ++k) Li22r[k * 36 + lane] = y[k];
-    if (lane == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
-  }
-  __syncthreads();
-  // ---- S5: Li21 = -Li22 (L21 Li11): LiT[m][32 + r] = -sum_t Li22r[r][t] WT[m][t]
-  for (int i = tid; i < 32 * 32; i += NT) {
-    const int m = i >> 5, r = i & 31;
-    LiT[m * RLD + 32 + r] = -dot32(Li22r + r * 36, WT + m * 36);
-  }
-  __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------- blocked diagonal block (v2)
+// ---------------------------------------------------------------------------------------------- blocked diagonal block
 // 64x64 factor + inverse as 4 panels of 16 columns.  The 16x16 pivot block is factored AND inverted by one warp
 // entirely in registers (row / inverse column per lane, operands exchanged with shuffles: no shared-memory round
 // trips on the 16-step dependency chain); the panel solve, the trailing update and the off-diagonal blocks of the
-// inverse are small products spread over all 256 threads with rolled loops.  Measured: the 32x32 smem-resident
-// version above spends ~700 cycles per elimination step; this one ~100.
+// inverse are small products spread over all 256 threads with rolled loops.  Measured: an earlier
+// shared-memory-resident 32x32 version spent ~700 cycles per elimination step; this one ~100.
 // D: row-major, stride RLD (lower triangle valid on entry; L in the lower triangle on exit, upper part untouched).
 // LiT[k][c] = Linv[c][k] (stride RLD).  scratch: >= DIAG2_SCRATCH_FLOATS floats.  All CTA threads must call it.
 constexpr int I16_LD = 20;

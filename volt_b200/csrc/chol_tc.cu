@@ -20,6 +20,15 @@
 namespace volt {
 namespace tc {
 
+// -DVOLT_PROFILE (tools/build.sh --profile -> libvolt_prof.so): thread 0 of CTA 0 accumulates clock64() per kernel
+// segment and drops the 12 counters into the first floats of `alpha`; read by tools/seg_probe.py.  Never on in the
+// shipped library.
+#ifdef VOLT_PROFILE
+#define TICK(i) do { if (threadIdx.x == 0) { const long long _n = clock64(); seg[i] += _n - tlast; tlast = _n; } } while (0)
+#else
+#define TICK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
@@ -65,6 +74,10 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   c.tmem = *s_tmem_p;
   const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
 
+#ifdef VOLT_PROFILE
+  long long seg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#endif
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     for (int i = tid; i < Tp; i += NT) {
       float v = 0.f;
@@ -95,7 +108,9 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
         for (int ch = 0; ch < nch; ++ch) {
           const int r_base = R0 + ch * CM;
           const int gr = r_base + row;
+          TICK(0);
           const bool have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
+          TICK(1);
           float s[32];
           if (have) {
             tmem_ld32(c.tmem + t_lane + (uint32_t)c0, s);
@@ -110,6 +125,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #pragma unroll
             for (int q = 0; q < 32; ++q) s[q] = 0.f;
           }
+          TICK(2);
           if (ch == 0) {
             // rows < 64 are the diagonal block (-> Ct); the other rows park their 32 values in the free tail of X so
             // that no accumulator registers stay live across the warp-level factorisation below
@@ -124,7 +140,9 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
               for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
             __syncthreads();
+            TICK(3);
             diag64_block_v2<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
+            TICK(4);
             if (tid < NB && R0 + tid < T) logdet_part += logf(c.diagl[tid]);
             for (int idx = tid; idx < NB * NB; idx += NT) {
               const int r = idx >> 6, cc = idx & 63;
@@ -173,8 +191,10 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
             }
             __syncthreads();  // LiT / tmp / stash (aliasing X) are dead from here on; Linv operand staged
           }
+          TICK(5);
           float o[32];
           trsm_tc(c, s, o, row, half_id);
+          TICK(6);
           {
             // warp-uniform: the warp's 32 rows start at a multiple of 32 and Tp, R0 are multiples of 64
             const int g0 = r_base + 32 * (warp & 3);
@@ -223,13 +243,16 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
         for (int ch = 0; ch < nch; ++ch) {
           const int m_base = ch * CM;
           const int m = m_base + row;
+          TICK(7);
           gemm_tc<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
+          TICK(8);
           float s[32], o[32];
           tmem_ld32(c.tmem + t_lane + (uint32_t)c0, s);
           tc_fence_before();
 #pragma unroll
           for (int q = 0; q < 32; ++q) s[q] = -s[q];
           trsm_tc(c, s, o, row, half_id);
+          TICK(9);
           float hdot = 0.f;
           {
             const int g0 = m_base + 32 * (warp & 3);
@@ -252,6 +275,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
       }
     }
 
+    TICK(10);
     // =============================== reductions and outputs (identical to the SIMT kernel)
     float zz = 0.f, aa = 0.f, ar = 0.f, z22 = 0.f, z12 = 0.f;
     for (int i = tid; i < T; i += NT) {
@@ -293,6 +317,10 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
     __syncthreads();
   }
 
+#ifdef VOLT_PROFILE
+  TICK(11);
+  if (tid == 0 && blockIdx.x == 0 && p.z_out == nullptr && p.alpha) for (int i = 0; i < 12; ++i) p.alpha[i] = (float)seg[i];
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(c.tmem) : "memory");
