@@ -399,3 +399,92 @@ def test_long_series_c5_shape(vb, T):
     assert relerr(out["draw_noise"][0], ref["draw_noise"]) < 2e-3
     assert relerr(out["alpha"][0], ref["alpha"]) < 2e-3
     assert relerr(out["scalars"][0, 2], ref["logdet"]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ properties / edge cases
+def test_vol_cov_symmetric_psd_and_structure(vb):
+    """KAT-1/2 on the GPU output: K = C diag(w sigma^2) C^T, symmetric, PSD, chol(K) = C diag(sqrt(w sigma^2))."""
+    T = 96
+    x, vol, _ = O.synth_series(2, T, seed=9)
+    K = vb.ops.vol_cov(x.cuda(), vol.cuda()).cpu().double()
+    assert torch.equal(K, K.transpose(-1, -2))
+    w = (x[1] - x[0]).double() * torch.ones(T, dtype=torch.float64)
+    w[0] *= 0.5
+    w[-1] *= 0.5
+    C = torch.tril(torch.ones(T, T, dtype=torch.float64))
+    for b in range(2):
+        d = w * vol[b].double() ** 2
+        torch.testing.assert_close(K[b], C @ torch.diag(d) @ C.T, rtol=1e-5, atol=1e-9)
+        assert float(torch.linalg.eigvalsh(K[b]).min()) > -1e-9
+
+
+@pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma", "meanrevert"])
+def test_rollout_short_history_and_replication(vb, mean_func):
+    """Window longer than the history (k > n: left padding with y[0]) and invariance to replicating draws."""
+    n, S, H, k = 16, 5, 6, 25
+    x, vol, logy = O.synth_series(1, n, seed=2)
+    g = torch.Generator().manual_seed(4)
+    pred_vol = vol[:, -1:, None] * torch.exp(0.2 * torch.randn(1, S, H, generator=g))
+    eps = torch.randn(1, S, H, generator=g)
+    kw = dict(mean_kind=mean_func, k=k)
+    if mean_func == "meanrevert":
+        kw.update(mr_theta=0.3, mr_latent=logy[0].mean())
+    out, _, _ = vb.ops.rollout(x, logy, vol, pred_vol, eps=eps, **kw)
+    px = torch.cat((logy[:, :1], logy), -1).exp()
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    if mean_func != "meanrevert":
+        want = O.rollouts(x, px[0], vol[0].log(), test_x, pred_vol[0], eps[0], k, mean_kind=mean_func)
+        assert relerr(out[0], want) < 1e-3
+    rep, _, _ = vb.ops.rollout(x, logy, vol, pred_vol.repeat(1, 40, 1), eps=eps.repeat(1, 40, 1), **kw)
+    assert torch.equal(rep[0, :S], out[0]) and torch.equal(rep[0, -S:], out[0])
+
+
+def test_rollout_joint_given_mean_vs_oracle(vb):
+    """One-shot multi-point draw (rollout_utils.GeneratePrediction with H test points, parametric mean)."""
+    n, S, H = 80, 9, 11
+    x, vol, logy = O.synth_series(1, n, seed=12)
+    g = torch.Generator().manual_seed(8)
+    pred_vol = vol[0, -1] * torch.exp(0.2 * torch.randn(S, H, generator=g))
+    eps = torch.randn(S, H, generator=g)
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    mtrain, mtest = torch.full((n,), 2.3), torch.linspace(2.3, 2.4, H)
+    out, dinfo, _ = vb.ops.rollout(x, logy, vol, pred_vol.reshape(1, S, H), eps=eps.reshape(1, S, H), mean_kind="given", k=0,
+                                   resid_given=(logy[0] - mtrain).reshape(1, n), mean_test=mtest.reshape(1, H), joint=True)
+    # oracle: dense algebra of rollout_utils.py:6-53 with a parametric mean
+    full_x = torch.cat((x, test_x))
+    want = torch.empty(S, H)
+    for s_ in range(S):
+        Kf = O.vol_kernel(full_x.double(), torch.cat((vol[0], pred_vol[s_])).double())
+        Ktr, Kx, Kte = Kf[:n, :n], Kf[:n, n:], Kf[n:, n:]
+        L = torch.linalg.cholesky(Ktr)
+        mean = Kx.T @ torch.cholesky_solve((logy[0] - mtrain).double().unsqueeze(-1), L) + mtest.double().unsqueeze(-1)
+        cov = Kte - Kx.T @ torch.cholesky_solve(Kx, L)
+        want[s_] = (mean + torch.linalg.cholesky(cov) @ eps[s_].double().unsqueeze(-1)).squeeze(-1).float()
+    assert relerr(out[0], want) < 1e-3
+
+
+def test_c_abi_argument_errors(vb):
+    lib = vb._lib.load()
+    x = torch.arange(8, dtype=torch.float32).cuda()
+    out = torch.empty(8, 8).cuda()
+    assert lib.volt_vol_cov(None, 0, x.data_ptr(), 1, 1, 8, None, 0, out.data_ptr(), None) == -1
+    assert b"null" in lib.volt_last_error()
+    assert lib.volt_vol_cov(x.data_ptr(), 0, x.data_ptr(), 1, 1, 1, None, 0, out.data_ptr(), None) == -1   # T < 2
+    assert lib.volt_ewma(x.data_ptr(), 1, 8, 0, out.data_ptr(), None) == -1                                 # k < 1
+    assert lib.volt_potrf(out.data_ptr(), 64, 4, None, 0, 1, 8, 0.0, 3, out.data_ptr(), 64, 8, None, None, None) == -1  # lda < T
+
+
+def test_engineered_not_psd_data_model(vb):
+    """A zero-volatility segment makes K exactly singular: with (almost) no noise the factorisation must report it
+    the way cholesky_ex does, and the psd_safe_cholesky retry must rescue it."""
+    T = 64
+    x = torch.arange(T) / 252.0
+    vol = torch.full((1, T), 0.2)
+    vol[0, 20:30] = 0.0
+    resid = 0.01 * torch.randn(1, T, generator=torch.Generator().manual_seed(0))
+    K = O.vol_kernel(x, vol[0]) - 1e-4 * torch.eye(T)       # dense input, pushed slightly indefinite
+    bad = vb.ops.mll_grad("dense", None, K.cuda(), resid.cuda(), torch.zeros(1).cuda(), jitter=0.0, check=False)
+    _, info_t = torch.linalg.cholesky_ex(K)
+    assert int(bad["info"][0]) > 0 and int(info_t) > 0
+    ok = vb.ops.mll_grad("dense", None, K.cuda(), resid.cuda(), torch.zeros(1).cuda(), jitter=1e-4, check=False)
+    assert int(ok["info"][0]) == 0 and float(ok["scalars"][0, 7]) >= 1e-4
