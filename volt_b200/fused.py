@@ -1,0 +1,162 @@
+"""Device-resident Adam loops for the two training loops on the hot path.
+
+`TrainVoltMagpieModel` with a moving-average mean trains ONE scalar (the likelihood raw_noise, train_utils.py:201-203)
+against a fixed covariance and a fixed residual; `TrainVolModel` trains (raw_noise, raw_vol) of the BM vol model.
+Both are `train_iters` repetitions of [transform parameters -> exact MLL + analytic gradient (one launch of the fused
+CUDA kernel) -> Adam update].  Here one iteration is captured in a CUDA graph and replayed: no per-iteration host
+synchronisation, H2D/D2H traffic or Python-side autograd.  The arithmetic is the reference's: GPyTorch's parameter
+transforms, MLL / T, torch.optim.Adam defaults (betas 0.9 / 0.999, eps 1e-8, no weight decay, bias correction).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+from ._lib import S_ALAL, S_ALR, S_DNOISE, S_MLL, S_TRINV, VOLT_NSCALARS
+from .means import _MAMean
+
+_B1, _B2, _EPS = 0.9, 0.999, 1e-8
+
+
+class _Adam:
+    """torch.optim.Adam (defaults) on a few device scalars, written so that a CUDA graph can capture it."""
+
+    def __init__(self, params, lr):
+        self.params, self.lr = params, lr
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.t = torch.zeros((), device=params[0].device)
+
+    def step(self, grads):
+        self.t += 1.0
+        bc1 = 1.0 - torch.pow(torch.full_like(self.t, _B1), self.t)
+        bc2 = 1.0 - torch.pow(torch.full_like(self.t, _B2), self.t)
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            m.mul_(_B1).add_(g, alpha=1.0 - _B1)
+            v.mul_(_B2).addcmul_(g, g, value=1.0 - _B2)
+            denom = v.sqrt() / bc2.sqrt() + _EPS
+            p.sub_((self.lr / bc1) * (m / denom))
+
+
+def _run(iteration, train_iters, printing, scal):
+    """Warm up eagerly (workspace allocation is not capturable), capture one iteration, replay the rest."""
+    done = 0
+    for _ in range(min(2, train_iters)):
+        iteration()
+        done += 1
+        if printing and (done - 1) % 50 == 0:
+            print("Iter %d/%d - Loss: %.3f" % (done, train_iters, -float(scal[0, S_MLL])))
+    if done == train_iters:
+        return
+    graph = None
+    try:
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            iteration()
+        graph = g
+        done += 1  # capture does not execute; account for the replay below
+        graph.replay()
+    except Exception:  # noqa: BLE001  (capture unsupported: stay eager on the GPU)
+        graph = None
+    while done < train_iters:
+        if graph is not None:
+            graph.replay()
+        else:
+            iteration()
+        done += 1
+        if printing and (done - 1) % 50 == 0:
+            print("Iter %d/%d - Loss: %.3f" % (done, train_iters, -float(scal[0, S_MLL])))
+
+
+def _fit_noise_ma(model, likelihood, train_x, target, lr, train_iters, printing):
+    dev = ops._dev()
+    lib = _lib.load()
+    spec = model.train_cov.fused()
+    if spec is None or spec[0] != "vol":
+        return False
+    _, x, vol = spec
+    T = target.shape[-1]
+    xd = ops._f32(x, dev).reshape(-1)
+    vd = ops._f32(vol, dev).reshape(1, T)
+    with torch.no_grad():
+        resid = ops._f32(target - model.mean_module(train_x), dev).reshape(1, T)
+    raw = ops._f32(likelihood.raw_noise, dev).reshape(1).clone()
+    opt = _Adam([raw], lr)
+    noise = torch.empty(1, device=dev)
+    scal = torch.empty(1, VOLT_NSCALARS, device=dev)
+    alpha = torch.empty(1, T, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def iteration():
+        torch.add(F.softplus(raw), 1e-4, out=noise)
+        _lib.check(lib.volt_mll_grad_vol(xd.data_ptr(), 0, vd.data_ptr(), ops.VOL_SIGMA, resid.data_ptr(), noise.data_ptr(), 0, 1, T,
+                                         1e-6, 3, scal.data_ptr(), alpha.data_ptr(), info.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "volt_mll_grad_vol")
+        bad.add_(info.ne(0).to(torch.int32))
+        opt.step([-(scal[0, S_DNOISE] * torch.sigmoid(raw))])   # d(-mll)/d raw_noise
+
+    _run(iteration, train_iters, printing, scal)
+    if int(bad) != 0:
+        raise ops.NotPSDError("training: covariance not positive definite after jitter retries")
+    with torch.no_grad():
+        likelihood.raw_noise.data = raw.to(likelihood.raw_noise.device).reshape(likelihood.raw_noise.shape)
+    return True
+
+
+def _fit_bmgp(model, likelihood, train_x, target, lr, train_iters, printing):
+    dev = ops._dev()
+    lib = _lib.load()
+    T = target.shape[-1]
+    xd = ops._f32(train_x, dev).reshape(-1)
+    yd = ops._f32(target, dev).reshape(1, T)
+    cov = model.covar_module
+    raw_noise = ops._f32(likelihood.raw_noise, dev).reshape(1).clone()
+    raw_vol = ops._f32(cov.raw_vol, dev).reshape(1).clone()
+    opt = _Adam([raw_noise, raw_vol], lr)   # registration order: likelihood first (ExactGP), then covar_module
+    noise, vol = torch.empty(1, device=dev), torch.empty(1, device=dev)
+    resid = torch.empty(1, T, device=dev)
+    scal = torch.empty(1, VOLT_NSCALARS, device=dev)
+    alpha = torch.empty(1, T, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def iteration():
+        torch.add(F.softplus(raw_noise), 1e-4, out=noise)
+        torch.sigmoid(raw_vol, out=vol)
+        torch.add(yd, 0.5 * vol * vol * xd, out=resid)          # y - (-1/2 vol^2 x), BMGP.py:20-21
+        _lib.check(lib.volt_mll_grad_bm(xd.data_ptr(), vol.data_ptr(), 0, resid.data_ptr(), noise.data_ptr(), 0, 1, T, 1e-6, 3,
+                                        scal.data_ptr(), alpha.data_ptr(), info.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream), "volt_mll_grad_bm")
+        bad.add_(info.ne(0).to(torch.int32))
+        s = scal[0]
+        d_noise = s[S_DNOISE]
+        # kernel scale: dMLL/ds = 1/2 [(alpha.r - noise alpha.alpha) - (T - noise tr A^-1)] / (s T)
+        d_scale = 0.5 * ((s[S_ALR] - noise * s[S_ALAL]) - (T - noise * s[S_TRINV])) / (vol * T)
+        # mean path: dMLL/dresid = -alpha / T, dresid/dvol = vol x
+        d_mean = (-(alpha[0] / T) * (vol * xd)).sum()
+        g_vol = (d_scale + d_mean) * vol * (1.0 - vol)          # sigmoid'
+        g_noise = d_noise * torch.sigmoid(raw_noise)
+        opt.step([-g_noise.reshape(1), -g_vol.reshape(1)])
+
+    _run(iteration, train_iters, printing, scal)
+    if int(bad) != 0:
+        raise ops.NotPSDError("training: covariance not positive definite after jitter retries")
+    with torch.no_grad():
+        likelihood.raw_noise.data = raw_noise.to(likelihood.raw_noise.device).reshape(likelihood.raw_noise.shape)
+        cov.raw_vol.data = raw_vol.to(cov.raw_vol.device).reshape(cov.raw_vol.shape)
+    return True
+
+
+def try_fused_loop(model, likelihood, train_x, target, lr, train_iters, printing):
+    """Returns True when the loop was run on the device-resident path, False when the caller must use the generic one."""
+    from .models import BMGP, _VoltBase
+
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    if isinstance(model, _VoltBase) and isinstance(model.mean_module, _MAMean) and target.ndim == 1 \
+            and trainable == ["likelihood.noise_covar.raw_noise"] and model.likelihood is likelihood:
+        return _fit_noise_ma(model, likelihood, train_x, target, lr, train_iters, printing)
+    if isinstance(model, BMGP) and target.ndim == 1 and model.likelihood is likelihood \
+            and trainable == ["likelihood.noise_covar.raw_noise", "covar_module.raw_vol"]:
+        return _fit_bmgp(model, likelihood, train_x, target, lr, train_iters, printing)
+    return False

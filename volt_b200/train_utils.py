@@ -10,6 +10,15 @@ from .models import BMGP, VoltMagpie, VoltronGP
 
 
 def _adam_mll_loop(model, likelihood, train_x, target, lr, train_iters, printing):
+    """`for i in range(train_iters): loss = -mll(model(train_x), y); loss.backward(); optimizer.step()`
+    (train_utils.py:84-94, 131-141, 243-254).  The two loops the shipped drivers spend their time in -- the noise-only
+    fit of the MA-mean data model and the (raw_noise, raw_vol) fit of the BM vol model -- run as a device-resident loop
+    (fused.py: one CUDA-graph replay per Adam iteration, no host round trips); every other configuration (parametric
+    means) takes the generic autograd path below."""
+    from . import fused
+
+    if train_iters > 0 and fused.try_fused_loop(model, likelihood, train_x, target, lr, train_iters, printing):
+        return
     optimizer = torch.optim.Adam([{"params": model.parameters()}], lr=lr)
     mll = gp.ExactMarginalLogLikelihood(likelihood, model)
     print_every = 50
