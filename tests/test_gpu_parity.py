@@ -488,3 +488,37 @@ def test_engineered_not_psd_data_model(vb):
     assert int(bad["info"][0]) > 0 and int(info_t) > 0
     ok = vb.ops.mll_grad("dense", None, K.cuda(), resid.cuda(), torch.zeros(1).cuda(), jitter=1e-4, check=False)
     assert int(ok["info"][0]) == 0 and float(ok["scalars"][0, 7]) >= 1e-4
+
+
+def test_rollout_singular_training_block_takes_jitter(vb):
+    """SURVEY section 7 hard part 3: a zero-vol segment duplicates rows of K_tr (exactly singular).  The reference's
+    psd_safe_cholesky(K_tr, jitter=1e-4) adds jitter only if LAPACK reports failure, and on a singular matrix the
+    computed pivot is rounding noise of either sign (torch 2.11 on CPU returns info == 0 and a meaningless factor for
+    this input), so the reference outcome is not reproducible.  The GPU path fails a pivot that is <= 8 eps A_ii and
+    therefore takes the jitter branch deterministically: compare with the oracle forced down that branch."""
+    n, S, H, k = 48, 7, 4, 10
+    x, vol, logy = O.synth_series(1, n, seed=21)
+    vol = vol.clone()
+    vol[0, 10:20] = 0.0
+    g = torch.Generator().manual_seed(5)
+    pred_vol = 0.2 * torch.exp(0.1 * torch.randn(1, S, H, generator=g))
+    eps = torch.randn(1, S, H, generator=g)
+    out, dinfo, sinfo = vb.ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind="ewma", k=k, check=False)
+    assert int(sinfo[0]) == 0 and int((dinfo & 5).sum()) == 0          # rescued by the retry, not reported as failure
+    assert bool(torch.isfinite(out).all())
+    px = torch.cat((logy[:, :1], logy), -1).exp()
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    orig = O.psd_safe_cholesky
+
+    def forced(A, jitter=None, **kw):
+        if A.shape[-1] > 1:   # K_tr: take the jitter branch unconditionally
+            return torch.linalg.cholesky(A + 1e-4 * torch.eye(A.shape[-1], dtype=A.dtype))
+        return orig(A, jitter=jitter, **kw)
+
+    O.psd_safe_cholesky = forced
+    try:
+        lv = vol[0].clamp_min(1e-30).log()   # exp(log(1e-30))^2 underflows to 0 in float32, like the zero vol itself
+        want = O.rollouts(x.double(), px[0].double(), lv.double(), test_x.double(), pred_vol[0].double(), eps[0].double(), k)
+    finally:
+        O.psd_safe_cholesky = orig
+    assert relerr(out[0], want) < 1e-3

@@ -32,6 +32,7 @@ struct LargeParams {
   float* z;            // (Tp): residual, overwritten by z = L^-1 r
   float* alpha;        // (Tp)
   float* acc;          // [0] sum log L_ii, [1] tr(A^-1)
+  float* origd;        // (Tp) original diagonal of A (pivot failure predicate)
   int* flag;           // first failing pivot index, -1 = none
 };
 
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) large_build_kernel(LargeParams p) {
   if (threadIdx.x == 0) {
     p.z[i] = (i < p.T) ? p.resid[i] : 0.f;
     p.alpha[i] = 0.f;
+    p.origd[i] = gen_large(p, i, i);
     p.Ut[(size_t)i * p.Tp + i] = 1.f;
     if (i == 0) { p.acc[0] = 0.f; p.acc[1] = 0.f; *p.flag = -1; }
   }
@@ -115,8 +117,10 @@ __global__ void __launch_bounds__(NT, 1) large_diag_kernel(LargeParams p, int j)
     c.Ct[r * CLD + cc] = p.W[(size_t)(R0 + r) * ld + R0 + cc];
   }
   if (tid == 0) *c.flag = -1;
+  if (tid < NB) c.tmp[tid] = p.origd[R0 + tid];
   __syncthreads();
-  diag64_block_v2<CLD>(c.Ct, sh.LiT, sh.tmpbuf, c.diagl, c.flag, R0);
+  diag64_block_v2<CLD>(c.Ct, sh.LiT, sh.tmpbuf, c.diagl, c.tmp, c.flag, R0);
+  __syncthreads();
   float* dj = p.dinv + (size_t)j * NB * NB;
   for (int idx = tid; idx < NB * NB; idx += NT) {
     const int r = idx >> 6, cc = idx & 63;
@@ -267,7 +271,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   if (s) return s;
   s = get_workspace(tp2 * sizeof(float), &u, 10);
   if (s) return s;
-  const size_t aux_fl = (size_t)p.nb * NB * NB + 2 * (size_t)p.Tp + 16;
+  const size_t aux_fl = (size_t)p.nb * NB * NB + 3 * (size_t)p.Tp + 16;
   s = get_workspace(aux_fl * sizeof(float), &aux, 11);
   if (s) return s;
   p.W = (float*)w;
@@ -275,7 +279,8 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   p.dinv = (float*)aux;
   p.z = p.dinv + (size_t)p.nb * NB * NB;
   p.alpha = p.z + p.Tp;
-  p.acc = p.alpha + p.Tp;
+  p.origd = p.alpha + p.Tp;
+  p.acc = p.origd + p.Tp;
   p.flag = reinterpret_cast<int*>(p.acc + 4);
   if (mp.kind == KIND_VOL) p.V = mp.V + (size_t)b * mp.T;
   else if (mp.kind == KIND_BM) { p.V = mp.x; }

@@ -135,13 +135,14 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+              if (half_id == 0) c.tmp[row] = gen_entry(p, b, gr, gr, c.Vs, sc, dadd);   // original A_ii for the pivot test
             } else {
 #pragma unroll
               for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
             __syncthreads();
             TICK(3);
-            diag64_block_v2<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.flag, R0);
+            diag64_block_v2<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.tmp, c.flag, R0);
             TICK(4);
             if (tid < NB && R0 + tid < T) logdet_part += logf(c.diagl[tid]);
             for (int idx = tid; idx < NB * NB; idx += NT) {

@@ -9,11 +9,12 @@
 // their leading n x n block and the first n entries of every appended column (V[0:n]).  Writing
 // L = [[L11, 0], [1 u^T, L22]] with u = L11^-1 V[0:n], the shared part (L11, u, z1 = L11^-1 r[0:n]) is computed ONCE per
 // series by the batched potrf kernel (chol_batched.cu); the per-draw part is the bordered update
-//      d_a = (V_s[n+a] - u.u) - sum_{t<a} f_t^2,  l_a = sqrt(d_a),  f_a = d_a / l_a   (= L22[a', a] for every a' > a),
+//      d_a = (V_s[n+a] + jitter - u.u) - sum_{t<a} f_t^2,  l_a = sqrt(d_a),
+//      f_a = (V_s[n+a] - u.u - sum_{t<a} f_t^2) / l_a   (= L22[a', a] for every a' > a; = d_a / l_a without jitter),
 //      w_a = (r_a - u.z1 - sum_{t<a} f_t w_t) / l_a,   q_a = (V_s[n+a] - u.u - sum_{t<a} f_t q_t) / l_a,
 //      mean = u.z1 + sum q_a w_a + m_test,   cov = V_test - u.u - sum q_a^2,
 // i.e. exactly the rows a dense left-looking Cholesky would append (every entry of column a of L22 is the same
-// floating-point expression d_a / l_a, so only running sums are kept).  No O(T) closed form is used.
+// floating-point expression, so only running sums are kept).  No O(T) closed form is used.
 #include "params.cuh"
 
 namespace volt {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
           const float d = (Ca + jit_s) - F2;  // jit_s: jitter the shared block needed (whole-diagonal, as psd_safe_cholesky)
           if (!(d > 0.f)) flags |= 1;
           const float l = sqrtf(d);
-          const float f = d / l;
+          const float f = (Ca - F2) / l;   // off-diagonal entries of column a carry no jitter (f == d / l when jit_s == 0)
           const float wa = (r_prev - uz - FW) / l;
           const float qa = (Ca - FQ) / l;
           F2 = fmaf(f, f, F2);
