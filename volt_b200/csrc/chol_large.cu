@@ -85,7 +85,7 @@ __device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_t
   if ((s_u32(base) & 1023u) != 0u) __trap();
   if (need_tmem) {
     if (threadIdx.x < 32) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s_u32(s_tmem_p)) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s_u32(s_tmem_p)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
@@ -101,7 +101,7 @@ __device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_t
 __device__ __forceinline__ void cta_teardown(Shared& sh) {
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(sh.c.tmem) : "memory");
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(sh.c.tmem) : "memory");
 }
 constexpr size_t LARGE_SMEM = VEC_OFF + sizeof(float) * (NB + 2 * NB + 32 + 12);
 

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   float* dinv = p.dinv + (size_t)blockIdx.x * nb * NB * NB;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s_u32(s_tmem_p)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s_u32(s_tmem_p)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(c.tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(c.tmem) : "memory");
 }
 
 }  // namespace tc

@@ -166,30 +166,67 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
   return true;
 }
 
+// 32 consecutive TMEM columns of this thread's lane <- registers (tcgen05.st, the mirror image of tmem_ld32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T : A operand read from tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+
+// TMEM column map of a CTA (256 columns allocated): accumulators and the TRSM A operand
+constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 64, TM_PHI = 128, TM_PLO = 192, TM_COLS = 256;
+
 // out = P . Linv^T where P (128 x 64, one row per (thread, column half)) is in registers `s`, Linv hi/lo already in c.Lr.
-// Two K halves (the warps holding columns 0..31 stage first, then the warps holding 32..63); result in acc1 -> `o`.
+// P is exactly in the layout tensor memory wants (lane = row), so it goes registers -> TMEM with tcgen05.st (raw fp32 as
+// the hi operand: the tensor core ignores the low 13 mantissa bits; lo = s - trunc(s)) and the product runs in the
+// TS form: no shared-memory staging of P and only the 2 KB B operand is read from shared memory per MMA.
 static __device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int row, int half_id) {
-  const int tid = threadIdx.x;
-  const uint32_t xb = s_u32(c.X), lb = s_u32(c.Lr);
+  const int tid = threadIdx.x, w = tid >> 5;
+  const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  {
+    uint32_t hi[32], lo[32];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (half_id == half) {
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        st_split(c.X, c.X + A_TILE, row, ch, make_float4(s[4 * ch], s[4 * ch + 1], s[4 * ch + 2], s[4 * ch + 3]));
+    for (int q = 0; q < 32; ++q) {
+      hi[q] = __float_as_uint(s[q]);
+      lo[q] = __float_as_uint(s[q] - __uint_as_float(hi[q] & 0xffffe000u));
     }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_ktile(c.tmem + 64, xb, xb + A_TILE, lb + half * B_TILE, lb + (2 + half) * B_TILE, half == 0);
-      umma_commit(c.bar);
-    }
-    wait_mma(c);
+    tmem_st32(c.tmem + lane_base + TM_PHI + (uint32_t)(half_id * 32), hi);
+    tmem_st32(c.tmem + lane_base + TM_PLO + (uint32_t)(half_id * 32), lo);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t lb = s_u32(c.Lr);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int kt = ks >> 2;
+      const uint64_t adv = (uint64_t)(2 * (ks & 3));
+      const uint64_t dbh = make_desc(lb + kt * B_TILE) + adv, dbl = make_desc(lb + (2 + kt) * B_TILE) + adv;
+      const uint32_t ah = c.tmem + TM_PHI + 8 * ks, al = c.tmem + TM_PLO + 8 * ks;
+      umma_tf32_ts(c.tmem + TM_ACC1, al, dbh, ks == 0 ? 0u : 1u);
+      umma_tf32_ts(c.tmem + TM_ACC1, ah, dbl, 1u);
+      umma_tf32_ts(c.tmem + TM_ACC1, ah, dbh, 1u);
+    }
+    umma_commit(c.bar);
+  }
+  wait_mma(c);
   tc_fence_after();
-  const int w = tid >> 5;
-  tmem_ld32(c.tmem + ((uint32_t)(32 * (w & 3)) << 16) + 64u + (uint32_t)(half_id * 32), o);
+  tmem_ld32(c.tmem + lane_base + TM_ACC1 + (uint32_t)(half_id * 32), o);
   tc_fence_before();
 }
 
