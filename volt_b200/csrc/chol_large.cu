@@ -78,7 +78,7 @@ __device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_t
   c.red = c.tmp + 2 * NB;         // 32
   c.flag = reinterpret_cast<int*>(c.red + 32);
   c.bar = reinterpret_cast<uint64_t*>(c.red + 36);
-  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 38);
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 40);   // c.bar holds two mbarriers (16 bytes)
   c.phase = 0;
   sh.LiT = reinterpret_cast<float*>(c.X + X_LIT);
   sh.tmpbuf = reinterpret_cast<float*>(c.X + X_TMP);
@@ -90,6 +90,7 @@ __device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_t
     }
     if (threadIdx.x == 0) {
       mbar_init(c.bar, 1);
+      mbar_init(c.bar + 1, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();

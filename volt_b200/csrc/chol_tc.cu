@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   c.red = c.tmp + 2 * NB;
   c.flag = reinterpret_cast<int*>(c.red + 32);
   c.bar = reinterpret_cast<uint64_t*>(c.red + 36);
-  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 38);
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 40);   // c.bar holds two mbarriers (16 bytes)
   c.phase = 0;
   float* LiT = reinterpret_cast<float*>(c.X + X_LIT);
   float* tmpbuf = reinterpret_cast<float*>(c.X + X_TMP);
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   }
   if (tid == 0) {
     mbar_init(c.bar, 1);
+    mbar_init(c.bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.Tp = (p.T + NB - 1) / NB * NB;
   p.nb = p.Tp / NB;
-  const size_t smem = tc::VEC_OFF + sizeof(float) * (size_t)(4 * p.Tp + NB + 2 * NB + 32 + 8);
+  const size_t smem = tc::VEC_OFF + sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12);
   if (smem > 227 * 1024) {
     set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);
     return VOLT_ERR_ARG;

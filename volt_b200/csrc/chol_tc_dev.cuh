@@ -10,7 +10,7 @@ constexpr int CLD = NB + 4;                   // Ct / LiT row stride (floats)
 constexpr uint32_t A_TILE = 128u * 128u;      // bytes of one 128-row x 32-float operand tile
 constexpr uint32_t B_TILE = 64u * 128u;       // bytes of one 64-row x 32-float operand tile
 // shared-memory map (byte offsets from a 1024-aligned base)
-constexpr uint32_t X_AHI = 0, X_ALO = A_TILE, X_BHI = 2 * A_TILE, X_BLO = 2 * A_TILE + B_TILE;
+constexpr uint32_t X_B0 = A_TILE;   // GEMM stage: raw A tile (16 KB) | B hi/lo buffer 0 (16 KB) | B hi/lo buffer 1 (16 KB)
 constexpr uint32_t X_BYTES = 2 * A_TILE + 2 * B_TILE;           // 48 KB GEMM stage; aliased by P (hi|lo) and LiT|tmp
 constexpr uint32_t X_LIT = 0, X_TMP = 64 * CLD * 4;             // LiT 17408 B, diag scratch 14336 B,
 constexpr uint32_t X_STASH = 32768;                             // 16 KB stash of the chunk-0 panel rows  (<= 48 KB)
@@ -96,13 +96,14 @@ struct Ctx {
   float* diagl; float* tmp; float* red; int* flag;
   uint64_t* bar;
   uint32_t tmem;     // TMEM base (128 columns: acc0 = [0,64), acc1 = [64,128))
-  uint32_t phase;    // parity of the next mbarrier completion to wait for
+  uint32_t phase;    // bit h = parity of the next completion of mbarrier h to wait for
 };
 
-__device__ __forceinline__ void wait_mma(Ctx& c) {
-  mbar_wait(c.bar, c.phase);
-  c.phase ^= 1u;
+__device__ __forceinline__ void wait_mma2(Ctx& c, int h) {
+  mbar_wait(c.bar + h, (c.phase >> h) & 1u);
+  c.phase ^= (1u << h);
 }
+__device__ __forceinline__ void wait_mma(Ctx& c) { wait_mma2(c, 0); }
 
 // 3xTF32 product of one k-tile (32 floats): D (+)= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T.  One thread issues.
 __device__ __forceinline__ void issue_ktile(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, bool first) {
@@ -114,56 +115,6 @@ __device__ __forceinline__ void issue_ktile(uint32_t tmem_d, uint32_t a_hi, uint
     umma_tf32(tmem_d, dah + adv, dbl + adv, 1u);
     umma_tf32(tmem_d, dah + adv, dbh + adv, 1u);
   }
-}
-
-// acc0 = A[a_row0 + r, k_lo:k_hi] . Bm[b_row0 + n, k_lo:k_hi]^T  on the tensor cores (r < 128, n < 64).
-// Returns false when the k-range is empty (acc0 untouched).
-template <bool PHASE_B>
-__device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_end, int b_row0, int k_lo, int k_hi, const float* dinv,
-                        const float* SB = nullptr) {
-  if (SB == nullptr) SB = S;  // B operand rows come from a second matrix in the large-matrix inverse sweep
-  const int tid = threadIdx.x;
-  const int nk = (k_hi - k_lo) / 32;
-  if (nk <= 0) return false;
-  float4 ra[4], rb[2];
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + NT * i, row = idx >> 3, chunk = idx & 7;
-      ra[i] = load_a<PHASE_B>(S, ld, a_row0 + row, a_row_end, k0 + chunk * 4, dinv);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + NT * i, row = idx >> 3, chunk = idx & 7;
-      rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + row) * ld + k0 + chunk * 4);
-    }
-  };
-  gload(k_lo);
-  for (int kt = 0; kt < nk; ++kt) {
-    if (kt > 0) wait_mma(c);  // the previous k-tile's MMAs have consumed the stage
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + NT * i;
-      st_split(c.X + X_AHI, c.X + X_ALO, idx >> 3, idx & 7, ra[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + NT * i;
-      st_split(c.X + X_BHI, c.X + X_BLO, idx >> 3, idx & 7, rb[i]);
-    }
-    if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t xb = s_u32(c.X);
-      issue_ktile(c.tmem, xb + X_AHI, xb + X_ALO, xb + X_BHI, xb + X_BLO, kt == 0);
-      umma_commit(c.bar);
-    }
-  }
-  wait_mma(c);
-  tc_fence_after();
-  return true;
 }
 
 // 32 consecutive TMEM columns of this thread's lane <- registers (tcgen05.st, the mirror image of tmem_ld32)
@@ -188,6 +139,105 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // TMEM column map of a CTA (256 columns allocated): accumulators and the TRSM A operand
 constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 64, TM_PHI = 128, TM_PLO = 192, TM_COLS = 256;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// acc0 = A[a_row0 + r, k_lo:k_hi] . Bm[b_row0 + n, k_lo:k_hi]^T  on the tensor cores (r < 128, n < 64).
+//
+// The loop is bound by the shared-memory port when both operands are read from shared memory (an M128 x N64 x K8 SS
+// MMA reads 6 KB per 32 ideal cycles and the 3-pass split reads every operand three times), so the A operand goes
+// through TENSOR MEMORY instead: per 32-float k-tile the CTA stores the raw A tile once in shared memory (coalesced
+// global loads), every thread reads back its own row / k-half (the tcgen05.st 32x32b layout: lane = row), splits it
+// (hi = raw bits: the tensor core ignores the low 13 mantissa bits; lo = a - trunc(a)) and writes both to TMEM; only
+// the 64-row B operand is staged hi/lo in shared memory and read by the MMAs (TS form).  A (in TMEM) and B (in
+// shared memory) are double-buffered, so the MMAs of tile kt overlap the staging of tile kt+1; mbarrier h guards the
+// reuse of buffer h (tcgen05.commit).  Returns false when the k-range is empty (acc0 untouched).
+template <bool PHASE_B>
+__device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_end, int b_row0, int k_lo, int k_hi, const float* dinv,
+                        const float* SB = nullptr) {
+  if (SB == nullptr) SB = S;  // B operand rows come from a second matrix in the large-matrix inverse sweep
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int nk = (k_hi - k_lo) / 32;
+  if (nk <= 0) return false;
+  const int row = 32 * (w & 3) + lane, half_id = w >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  uint8_t* RAW = c.X;                                   // 16 KB raw A tile, rows of 128 B, 16-byte chunks XOR-swizzled
+  float4 ra[4], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      ra[i] = load_a<PHASE_B>(S, ld, a_row0 + r, a_row_end, k0 + chunk * 4, dinv);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
+    }
+  };
+  gload(k_lo);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int h = kt & 1;
+    uint8_t* BH = c.X + X_B0 + h * (2 * B_TILE);
+    uint8_t* BL = BH + B_TILE;
+    if (kt >= 2) wait_mma2(c, h);   // MMA group kt-2 has consumed TMEM / shared-memory buffer h
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      *reinterpret_cast<float4*>(RAW + r * 128 + ((chunk ^ (r & 7)) << 4)) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + NT * i;
+      st_split(BH, BL, idx >> 3, idx & 7, rb[i]);
+    }
+    if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
+    __syncthreads();
+    {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = 4 * half_id + q;
+        const float4 v = *reinterpret_cast<const float4*>(RAW + row * 128 + ((chunk ^ (row & 7)) << 4));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hi[4 * q + j] = __float_as_uint(e[j]);
+          lo[4 * q + j] = __float_as_uint(e[j] - __uint_as_float(hi[4 * q + j] & 0xffffe000u));
+        }
+      }
+      tmem_st16(c.tmem + lane_base + TM_PHI + (uint32_t)(32 * h + 16 * half_id), hi);
+      tmem_st16(c.tmem + lane_base + TM_PLO + (uint32_t)(32 * h + 16 * half_id), lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t dbh = make_desc(s_u32(BH)), dbl = make_desc(s_u32(BL));
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t adv = (uint64_t)(2 * ks);
+        const uint32_t ah = c.tmem + TM_PHI + 32 * h + 8 * ks, al = c.tmem + TM_PLO + 32 * h + 8 * ks;
+        umma_tf32_ts(c.tmem + TM_ACC0, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+        umma_tf32_ts(c.tmem + TM_ACC0, ah, dbl + adv, 1u);
+        umma_tf32_ts(c.tmem + TM_ACC0, ah, dbh + adv, 1u);
+      }
+      umma_commit(c.bar + h);
+    }
+  }
+  wait_mma2(c, (nk - 1) & 1);
+  if (nk >= 2) wait_mma2(c, (nk - 2) & 1);
+  tc_fence_after();
+  return true;
+}
 
 // out = P . Linv^T where P (128 x 64, one row per (thread, column half)) is in registers `s`, Linv hi/lo already in c.Lr.
 // P is exactly in the layout tensor memory wants (lane = row), so it goes registers -> TMEM with tcgen05.st (raw fp32 as
