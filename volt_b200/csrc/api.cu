@@ -285,14 +285,44 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   float* d_scal = d_noise + n_noise;
   float* d_alpha = d_scal + (size_t)B * VOLT_NSCALARS;
   int* d_info = (int*)(d_alpha + bt);
-  cudaStream_t st = 0;
-  VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, st));
-  VOLT_CUDA(cudaMemcpyAsync(d_vol, vol, bt * 4, cudaMemcpyHostToDevice, st));
-  VOLT_CUDA(cudaMemcpyAsync(d_res, resid, bt * 4, cudaMemcpyHostToDevice, st));
-  VOLT_CUDA(cudaMemcpyAsync(d_noise, noise, n_noise * 4, cudaMemcpyHostToDevice, st));
-  s = volt_mll_grad_vol(d_x, 0, d_vol, VOLT_VOL_SIGMA, d_res, d_noise, noise_stride, B, T, jitter, max_tries, d_scal,
-                        alpha ? d_alpha : nullptr, d_info, st);
+  // Two-stage pipeline: the first wave of series (one per resident CTA slot) is copied and launched first, the copy of
+  // the remaining series overlaps its factorisation on a second stream.  Kernels stay on one stream (shared workspace).
+  static cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  static cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (!s_copy) {
+    VOLT_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    VOLT_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    VOLT_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    VOLT_CUDA(cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
+  }
+  void* vres = nullptr;
+  s = get_workspace(bt * sizeof(float), &vres, 1);   // reserve the prefix-sum buffer at full size (no regrow mid-pipeline)
   if (s) return s;
+  const int slots = 2 * sm_count();
+  const int B0 = (B >= 2 * slots) ? slots : B;
+  const size_t n0 = (size_t)B0 * T;
+  VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, s_copy));
+  VOLT_CUDA(cudaMemcpyAsync(d_noise, noise, n_noise * 4, cudaMemcpyHostToDevice, s_copy));
+  VOLT_CUDA(cudaMemcpyAsync(d_vol, vol, n0 * 4, cudaMemcpyHostToDevice, s_copy));
+  VOLT_CUDA(cudaMemcpyAsync(d_res, resid, n0 * 4, cudaMemcpyHostToDevice, s_copy));
+  VOLT_CUDA(cudaEventRecord(ev0, s_copy));
+  if (B0 < B) {
+    VOLT_CUDA(cudaMemcpyAsync(d_vol + n0, vol + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy));
+    VOLT_CUDA(cudaMemcpyAsync(d_res + n0, resid + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy));
+    VOLT_CUDA(cudaEventRecord(ev1, s_copy));
+  }
+  VOLT_CUDA(cudaStreamWaitEvent(s_comp, ev0, 0));
+  s = volt_mll_grad_vol(d_x, 0, d_vol, VOLT_VOL_SIGMA, d_res, d_noise, noise_stride, B0, T, jitter, max_tries, d_scal,
+                        alpha ? d_alpha : nullptr, d_info, s_comp);
+  if (s) return s;
+  if (B0 < B) {
+    VOLT_CUDA(cudaStreamWaitEvent(s_comp, ev1, 0));
+    s = volt_mll_grad_vol(d_x, 0, d_vol + n0, VOLT_VOL_SIGMA, d_res + n0, d_noise + (noise_stride ? (size_t)B0 * noise_stride : 0),
+                          noise_stride, B - B0, T, jitter, max_tries, d_scal + (size_t)B0 * VOLT_NSCALARS,
+                          alpha ? d_alpha + n0 : nullptr, d_info + B0, s_comp);
+    if (s) return s;
+  }
+  cudaStream_t st = s_comp;
   VOLT_CUDA(cudaMemcpyAsync(scalars, d_scal, (size_t)B * VOLT_NSCALARS * 4, cudaMemcpyDeviceToHost, st));
   if (alpha) VOLT_CUDA(cudaMemcpyAsync(alpha, d_alpha, bt * 4, cudaMemcpyDeviceToHost, st));
   if (info) VOLT_CUDA(cudaMemcpyAsync(info, d_info, (size_t)B * 4, cudaMemcpyDeviceToHost, st));

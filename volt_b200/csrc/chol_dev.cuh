@@ -164,7 +164,7 @@ __device__ void trtri64(const float* Ct, float* LiT, float* tmpbuf) {
 // diagonal >= 1e-4 for the noise-free rollout matrix at T = 8192).  NaNs fail the comparison as in LAPACK.
 constexpr float PIVOT_RTOL = 8.f * 1.1920929e-07f;
 constexpr int I16_LD = 20;
-constexpr int DIAG2_SCRATCH_FLOATS = 4 * 16 * I16_LD + 48 * 20 + 64;
+constexpr int DIAG2_SCRATCH_FLOATS = 4 * 16 * I16_LD + 16 * 52 + 48 * 20;   // I16 | XT | WT (diag64_block_v2)
 
 template <int RLD>
 __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, float* diagl, const float* origd, int o, int lane,
@@ -231,11 +231,35 @@ __device__ __forceinline__ float dotn(const float* a, const float* b, int n) {  
   return (s0 + s1) + (s2 + s3);
 }
 
+__device__ __forceinline__ float dot4(const float4 u, const float4 v, float acc) {
+  acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+  return acc;
+}
+// 2 x 2 register tile of dot products: rows a0/a1 against rows b0/b1 (n floats, n multiple of 4, 16-byte aligned)
+__device__ __forceinline__ void dot2x2(const float* a0, const float* a1, const float* b0, const float* b1, int n, float& r00, float& r01,
+                                       float& r10, float& r11) {
+  r00 = r01 = r10 = r11 = 0.f;
+  for (int t = 0; t < n; t += 4) {
+    const float4 u0 = *reinterpret_cast<const float4*>(a0 + t), u1 = *reinterpret_cast<const float4*>(a1 + t);
+    const float4 v0 = *reinterpret_cast<const float4*>(b0 + t), v1 = *reinterpret_cast<const float4*>(b1 + t);
+    r00 = dot4(u0, v0, r00); r01 = dot4(u0, v1, r01); r10 = dot4(u1, v0, r10); r11 = dot4(u1, v1, r11);
+  }
+}
+
+// Shared-memory traffic of this routine was 31 % of the kernel's shared wavefronts with one output per thread
+// (ncu, profiles/): every product below is register-tiled (2 x 2 dot tiles over rows {i, i+8} x {j, j+8}, 4 x 4 outer-
+// product tiles for the trailing update) and the lane maps keep each 8-lane LDS.128 phase either on 8 distinct bank
+// groups (row strides 68 and 20 floats) or on one broadcast address.
+constexpr int XT_LD = 52;
+constexpr int DIAG3_SCRATCH_FLOATS = 4 * 16 * I16_LD + 16 * XT_LD + 48 * 20;
+
 template <int RLD>
 __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* diagl, const float* origd, int* flag, int col0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* I16 = scratch;                          // 4 x (16 x I16_LD): row-major inverses of the pivot blocks
-  float* XP = scratch + 4 * 16 * I16_LD;         // 48 x 20: solved panel rows (row-major, 16 columns)
+  float* XT = scratch + 4 * 16 * I16_LD;         // 16 x XT_LD: solved panel, transposed (XT[t][row] = X[row][t])
+  float* WT = XT + 16 * XT_LD;                   // 48 x 20: per inverse block (16 x 20), WT[c][k] = W[k][c]
+  const int ti = tid & 7, tj = (tid >> 3) & 7, tg = tid >> 6;   // 2 x 2 tile owner: rows {ti, ti+8}, cols {tj, tj+8}, group tg
   int failc = -1;
   for (int p = 0; p < 4; ++p) {
     const int o = 16 * p;
@@ -250,34 +274,48 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
     }
     __syncthreads();
     if (R > 0) {
-      // ---- P2: panel solve X = S_panel Linv16^T (thread per (row, 4 columns); rows read before anybody writes)
-      const float* Ip = I16 + p * 16 * I16_LD;
-      for (int task = tid; task < R * 4; task += NT) {
-        const int rr = task >> 2, cq = (task & 3) * 4;
-        const float* srow = D + (o + 16 + rr) * RLD + o;
-        float4 out;
-        out.x = dotn(srow, Ip + (cq + 0) * I16_LD, 16);
-        out.y = dotn(srow, Ip + (cq + 1) * I16_LD, 16);
-        out.z = dotn(srow, Ip + (cq + 2) * I16_LD, 16);
-        out.w = dotn(srow, Ip + (cq + 3) * I16_LD, 16);
-        *reinterpret_cast<float4*>(XP + rr * 20 + cq) = out;
+      // ---- P2: panel solve X = S_panel Linv16^T, 16-row groups x (2 x 2 tiles); result kept transposed in XT
+      if (tid < R * 4) {
+        const float* a0 = D + (o + 16 + 16 * tg + ti) * RLD + o;
+        const float* b0 = I16 + p * 16 * I16_LD + tj * I16_LD;
+        float x00, x01, x10, x11;
+        dot2x2(a0, a0 + 8 * RLD, b0, b0 + 8 * I16_LD, 16, x00, x01, x10, x11);
+        const int r0 = 16 * tg + ti;
+        XT[tj * XT_LD + r0] = x00; XT[(tj + 8) * XT_LD + r0] = x01;
+        XT[tj * XT_LD + r0 + 8] = x10; XT[(tj + 8) * XT_LD + r0 + 8] = x11;
       }
       __syncthreads();
-      // ---- P3: write the panel back and apply the trailing update D[r][c] -= X[r].X[c] (c <= r)
-      for (int task = tid; task < R * 4; task += NT) {
-        const int rr = task >> 2, cq = (task & 3) * 4;
-        *reinterpret_cast<float4*>(D + (o + 16 + rr) * RLD + o + cq) = *reinterpret_cast<const float4*>(XP + rr * 20 + cq);
+      // ---- P3: write the panel back (row fastest) and apply the trailing update D[r][c] -= X[r].X[c] in 4 x 4 tiles
+      //      that touch the lower triangle (the strictly-upper entries a diagonal tile also updates are never read)
+      if (tid < R * 4) {
+        const int rr = (tid & 15) + 16 * (tid >> 6), cq = ((tid >> 4) & 3) * 4;
+        *reinterpret_cast<float4*>(D + (o + 16 + rr) * RLD + o + cq) =
+            make_float4(XT[cq * XT_LD + rr], XT[(cq + 1) * XT_LD + rr], XT[(cq + 2) * XT_LD + rr], XT[(cq + 3) * XT_LD + rr]);
       }
-      for (int task = tid; task < R * (R / 4); task += NT) {
-        const int rr = task / (R / 4), cq = (task - rr * (R / 4)) * 4;
-        if (cq <= rr) {
-          float4* dst = reinterpret_cast<float4*>(D + (o + 16 + rr) * RLD + o + 16 + cq);
+      const int nr = R >> 2, ntile = nr * (nr + 1) / 2;
+      if (tid < ntile) {
+        int ri = 0, ci = tid;
+        while (ci > ri) { ci -= ri + 1; ++ri; }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int t = 0; t < 16; ++t) {
+          const float4 a4 = *reinterpret_cast<const float4*>(XT + t * XT_LD + 4 * ri);
+          const float4 b4 = *reinterpret_cast<const float4*>(XT + t * XT_LD + 4 * ci);
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4* dst = reinterpret_cast<float4*>(D + (o + 16 + 4 * ri + i) * RLD + o + 16 + 4 * ci);
           float4 v = *dst;
-          const float* xr = XP + rr * 20;
-          v.x -= dotn(xr, XP + (cq + 0) * 20, 16);
-          v.y -= dotn(xr, XP + (cq + 1) * 20, 16);
-          v.z -= dotn(xr, XP + (cq + 2) * 20, 16);
-          v.w -= dotn(xr, XP + (cq + 3) * 20, 16);
+          v.x -= acc[i][0]; v.y -= acc[i][1]; v.z -= acc[i][2]; v.w -= acc[i][3];
           *dst = v;
         }
       }
@@ -288,19 +326,25 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
   // ---- inverse: off-diagonal 16-blocks by block distance d = pb - qb.
   //   W[r][c] = sum_{k in [16 qb, 16 pb)} L[16 pb + r][k] Linv[k][16 qb + c]  (= D row . LiT row, both contiguous)
   //   Linv[16 pb + r][16 qb + c] = - sum_k Linv16_pb[r][k] W[k][c]
-  float* WT = XP;  // reuse: per block (16 x 20), WT[c][k] = W[k][c]; 3 blocks at most per level -> 48 x 20
   for (int d = 1; d < 4; ++d) {
     const int nblk = 4 - d;
-    for (int task = tid; task < nblk * 256; task += NT) {
-      const int bi = task >> 8, r = (task >> 4) & 15, cc = task & 15;
-      const int qb = bi, pb = bi + d;
-      WT[(bi * 16 + cc) * 20 + r] = dotn(D + (16 * pb + r) * RLD + 16 * qb, LiT + (16 * qb + cc) * RLD + 16 * qb, 16 * d);
+    const int qb = tg, pb = tg + d;
+    if (tid < nblk * 64) {
+      const float* a0 = D + (16 * pb + ti) * RLD + 16 * qb;
+      const float* b0 = LiT + (16 * qb + tj) * RLD + 16 * qb;
+      float w00, w01, w10, w11;
+      dot2x2(a0, a0 + 8 * RLD, b0, b0 + 8 * RLD, 16 * d, w00, w01, w10, w11);
+      float* wt = WT + (tg * 16 + tj) * 20 + ti;
+      wt[0] = w00; wt[8 * 20] = w01; wt[8] = w10; wt[8 * 20 + 8] = w11;
     }
     __syncthreads();
-    for (int task = tid; task < nblk * 256; task += NT) {
-      const int bi = task >> 8, cc = (task >> 4) & 15, r = task & 15;
-      const int qb = bi, pb = bi + d;
-      LiT[(16 * qb + cc) * RLD + 16 * pb + r] = -dotn(I16 + pb * 16 * I16_LD + r * I16_LD, WT + (bi * 16 + cc) * 20, 16);
+    if (tid < nblk * 64) {
+      const float* a0 = I16 + pb * 16 * I16_LD + ti * I16_LD;
+      const float* b0 = WT + (tg * 16 + tj) * 20;
+      float l00, l01, l10, l11;
+      dot2x2(a0, a0 + 8 * I16_LD, b0, b0 + 8 * 20, 16, l00, l01, l10, l11);
+      float* lt = LiT + (16 * qb + tj) * RLD + 16 * pb + ti;
+      lt[0] = -l00; lt[8 * RLD] = -l01; lt[8] = -l10; lt[8 * RLD + 8] = -l11;
     }
     __syncthreads();
   }

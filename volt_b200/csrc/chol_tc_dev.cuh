@@ -283,7 +283,7 @@ static __device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int
 // Linv operand (B of the TRSM product): B[n][k] = Linv[n][k] = LiT[k][n], LiT with row stride CLD (floats).
 __device__ __forceinline__ void stage_linv_from_lit(Ctx& c, const float* LiT) {
   for (int q = threadIdx.x; q < 64 * 16; q += NT) {
-    const int n = q >> 4, kc = q & 15;  // kc: 16-byte chunk over k = 0..63
+    const int n = q & 63, kc = q >> 6;  // kc: 16-byte chunk over k = 0..63; n fastest: conflict-free LiT reads and tile stores
     const int k = kc * 4;
     const float4 v = make_float4(LiT[(k + 0) * CLD + n], LiT[(k + 1) * CLD + n], LiT[(k + 2) * CLD + n], LiT[(k + 3) * CLD + n]);
     const int kt = kc >> 3;
