@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libvolt_b200.so")
+# VOLT_B200_LIB: developer override used by tools/ab.sh to time experimental builds of the same ABI side by side
+LIB_PATH = os.environ.get("VOLT_B200_LIB") or os.path.join(HERE, "csrc", "libvolt_b200.so")
 
 VOLT_NSCALARS = 16
 S_MLL, S_DNOISE, S_LOGDET, S_INVQUAD, S_TRINV, S_ALAL, S_ALR, S_JITTER, S_Z2Z2, S_Z1Z2 = range(10)

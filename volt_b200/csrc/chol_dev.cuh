@@ -170,7 +170,7 @@ template <int RLD>
 __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, float* diagl, const float* origd, int o, int lane,
                                              int& failc) {
   const int r = lane & 15;
-  float a[16], inv16[16];
+  float a[16];
   {
     const float4* src = reinterpret_cast<const float4*>(D + (o + r) * RLD + o);
 #pragma unroll
@@ -179,6 +179,10 @@ __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, 
       a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
     }
   }
+  // Factor and invert in ONE unrolled loop: row c of the inverse (lane = column m: y[c] = Linv16[c][m]) only needs row
+  // c of L, which is final once column c has been eliminated, so its shuffles / FMAs are independent of the next
+  // elimination step and fill the latency gaps of that 16-step dependency chain (shfl -> rsqrt -> shfl -> fma).
+  float y[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     const float d = __shfl_sync(0xffffffffu, a[c], c);
@@ -186,11 +190,18 @@ __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, 
     float inv = rsqrtf(d);
     inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);  // one Newton step: 1/sqrt(d) to ~1 ulp
     const float l = d * inv;
-    inv16[c] = inv;
     const float lrc = (r == c) ? l : a[c] * inv;
     a[c] = lrc;
 #pragma unroll
     for (int k = c + 1; k < 16; ++k) a[k] = fmaf(-lrc, __shfl_sync(0xffffffffu, lrc, k), a[k]);
+    float acc0 = (c == r) ? 1.f : 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < c; ++t) {
+      const float lct = __shfl_sync(0xffffffffu, a[t], c);
+      if (t & 1) acc1 = fmaf(-lct, y[t], acc1);
+      else acc0 = fmaf(-lct, y[t], acc0);
+    }
+    y[c] = (acc0 + acc1) * inv;
   }
   if (lane < 16) {
     float dl = 0.f;
@@ -202,15 +213,6 @@ __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, 
     for (int q = 0; q < 4; ++q)
       dst[q] = make_float4(4 * q <= r ? a[4 * q] : 0.f, 4 * q + 1 <= r ? a[4 * q + 1] : 0.f, 4 * q + 2 <= r ? a[4 * q + 2] : 0.f,
                            4 * q + 3 <= r ? a[4 * q + 3] : 0.f);
-  }
-  // inverse: lane = column m, y[k] = Linv16[k][m]
-  float y[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    float acc = (k == r) ? 1.f : 0.f;
-#pragma unroll
-    for (int t = 0; t < k; ++t) acc = fmaf(-__shfl_sync(0xffffffffu, a[t], k), y[t], acc);
-    y[k] = acc * inv16[k];
   }
   if (lane < 16) {
 #pragma unroll

@@ -29,15 +29,20 @@ namespace tc {
 #define TICK(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
+// TRI = true: three CTAs per SM (128 TMEM columns, ~71 KB shared memory, single-buffered stages; chol_tc_dev.cuh);
+// TRI = false: two CTAs per SM with double-buffered stages (series too long for the small shared-memory map).
+template <bool TRI>
+__global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllParams p) {
+  constexpr uint32_t LOFF = TRI ? Y_L_OFF : L_OFF, CTOFF = TRI ? Y_CT_OFF : CT_OFF, VECOFF = TRI ? Y_VEC_OFF : VEC_OFF;
+  constexpr uint32_t XTMP = TRI ? Y_TMP : X_TMP, TCOLS = TRI ? T3_COLS : TM_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
   if ((s_u32(smem_raw) & 1023u) != 0u) __trap();  // SWIZZLE_128B operand tiles need a 1024-byte aligned base
   Ctx c;
   c.X = base;
-  c.Lr = base + L_OFF;
-  c.Ct = reinterpret_cast<float*>(base + CT_OFF);
-  c.Vs = reinterpret_cast<float*>(base + VEC_OFF);
+  c.Lr = base + LOFF;
+  c.Ct = reinterpret_cast<float*>(base + CTOFF);
+  c.Vs = reinterpret_cast<float*>(base + VECOFF);
   c.z = c.Vs + p.Tp;
   c.al = c.z + p.Tp;
   const bool has2 = (p.resid2 != nullptr);   // the second right-hand side (rollout prep) gets its own vector
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 40);   // c.bar holds two mbarriers (16 bytes)
   c.phase = 0;
   float* LiT = reinterpret_cast<float*>(c.X + X_LIT);
-  float* tmpbuf = reinterpret_cast<float*>(c.X + X_TMP);
+  float* tmpbuf = reinterpret_cast<float*>(c.X + XTMP);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane;   // accumulator row (TMEM lane) owned by this thread
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
   float* dinv = p.dinv + (size_t)blockIdx.x * nb * NB * NB;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s_u32(s_tmem_p)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(s_tmem_p)), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
@@ -110,7 +115,9 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
           const int r_base = R0 + ch * CM;
           const int gr = r_base + row;
           TICK(0);
-          const bool have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
+          bool have;
+          if constexpr (TRI) have = gemm_tc1<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
+          else have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           TICK(1);
           float s[32];
           if (have) {
@@ -137,6 +144,12 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
               for (int q = 0; q < 8; ++q)
                 *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
               if (half_id == 0) c.tmp[row] = gen_entry(p, b, gr, gr, c.Vs, sc, dadd);   // original A_ii for the pivot test
+            } else if constexpr (TRI) {
+              uint32_t u[32];   // park the rows in the accumulator columns (warp-uniform branch: rows >= 64 <=> (warp & 3) >= 2)
+#pragma unroll
+              for (int q = 0; q < 32; ++q) u[q] = __float_as_uint(s[q]);
+              tmem_st32(c.tmem + t_lane + (uint32_t)c0, u);
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
               for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
@@ -151,6 +164,7 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
               S[(size_t)(R0 + r) * ld + R0 + cc] = (cc <= r) ? c.Ct[r * CLD + cc] : 0.f;
               dinv[((size_t)j * NB + r) * NB + cc] = LiT[r * CLD + cc];
             }
+            if constexpr (TRI) __syncthreads();   // D aliases the Linv operand: every read of L_jj precedes the staging
             stage_linv_from_lit(c, LiT);
             if (rb) {
               const int cz = tid >> 2, part = tid & 3;
@@ -182,10 +196,14 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
               }
             }
             if (row >= NB) {
+              if constexpr (TRI) {
+                tmem_ld32(c.tmem + t_lane + (uint32_t)c0, s);
+              } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 v = stash[q * 128 + slot];
-                s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+                for (int q = 0; q < 8; ++q) {
+                  const float4 v = stash[q * 128 + slot];
+                  s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+                }
               }
             } else {
 #pragma unroll
@@ -195,13 +213,16 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
           }
           TICK(5);
           float o[32];
-          trsm_tc(c, s, o, row, half_id);
+          if constexpr (TRI) trsm_tc1(c, s, o, row, half_id);
+          else trsm_tc(c, s, o, row, half_id);
           TICK(6);
           {
             // warp-uniform: the warp's 32 rows start at a multiple of 32 and Tp, R0 are multiples of 64
             const int g0 = r_base + 32 * (warp & 3);
-            if (!(ch == 0 && (warp & 3) < 2) && g0 < Tp)
-              store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+            if (!(ch == 0 && (warp & 3) < 2) && g0 < Tp) {
+              if constexpr (TRI) store_block32_2p(reinterpret_cast<float*>(c.X) + warp * 640, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+              else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+            }
           }
           __syncthreads();
         }
@@ -246,19 +267,24 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
           const int m_base = ch * CM;
           const int m = m_base + row;
           TICK(7);
-          gemm_tc<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
+          if constexpr (TRI) gemm_tc1<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
+          else gemm_tc<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
           TICK(8);
           float s[32], o[32];
           tmem_ld32(c.tmem + t_lane + (uint32_t)c0, s);
           tc_fence_before();
 #pragma unroll
           for (int q = 0; q < 32; ++q) s[q] = -s[q];
-          trsm_tc(c, s, o, row, half_id);
+          if constexpr (TRI) trsm_tc1(c, s, o, row, half_id);
+          else trsm_tc(c, s, o, row, half_id);
           TICK(9);
           float hdot = 0.f;
           {
             const int g0 = m_base + 32 * (warp & 3);
-            if (g0 < R0) store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+            if (g0 < R0) {
+              if constexpr (TRI) store_block32_2p(reinterpret_cast<float*>(c.X) + warp * 640, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+              else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+            }
           }
           if (m < R0) {
             float dot = 0.f;
@@ -325,29 +351,20 @@ __global__ void __launch_bounds__(NT, 2) mll_batched_tc_kernel(MllParams p) {
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(c.tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(TCOLS) : "memory");
 }
 
 }  // namespace tc
 
-int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
-  p.Tp = (p.T + NB - 1) / NB * NB;
-  p.nb = p.Tp / NB;
-  const size_t smem = tc::VEC_OFF + sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12);
-  if (smem > 227 * 1024) {
-    set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);
-    return VOLT_ERR_ARG;
-  }
+template <bool TRI>
+static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(mll_batched_tc_kernel)");
     if (s) return s;
     attr_smem = smem;
   }
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
   int grid = sm_count() * per_sm;
   if (grid > p.B) grid = p.B;
   if (grid < 1) grid = 1;
@@ -357,8 +374,29 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   if (s) return s;
   p.scratch = reinterpret_cast<float*>(ws);
   p.dinv = p.scratch + (size_t)grid * p.Tp * p.Tp;
-  tc::mll_batched_tc_kernel<<<grid, NT, smem, st>>>(p);
+  tc::mll_batched_tc_kernel<TRI><<<grid, NT, smem, st>>>(p);
   return check_cuda(cudaGetLastError(), "mll_batched_tc_kernel");
+}
+
+int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
+  p.Tp = (p.T + NB - 1) / NB * NB;
+  p.nb = p.Tp / NB;
+  const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12);
+  const size_t smem_total = 233472, smem_cta_reserved = 1024;   // sm_100: 228 KB per SM, 1 KB reserved per resident CTA
+  // three resident CTAs per SM when the small shared-memory map fits three times (T <= ~640); VOLT_TC_CTAS=2 forces the
+  // double-buffered two-CTA kernel (A/B timing)
+  static const int force2 = [] { const char* e = getenv("VOLT_TC_CTAS"); return (e && e[0] == '2') ? 1 : 0; }();
+  const size_t smem3 = tc::Y_VEC_OFF + vec;
+  if (!force2 && 3 * (smem3 + smem_cta_reserved) <= smem_total) return launch_tc<true>(p, st, smem3, 3);
+  const size_t smem = tc::VEC_OFF + vec;
+  if (smem > 227 * 1024) {
+    set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);
+    return VOLT_ERR_ARG;
+  }
+  int per_sm = (int)(smem_total / (smem + smem_cta_reserved));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  return launch_tc<false>(p, st, smem, per_sm);
 }
 
 }  // namespace volt

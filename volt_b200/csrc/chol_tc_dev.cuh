@@ -170,16 +170,25 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
   uint8_t* RAW = c.X;                                   // 16 KB raw A tile, rows of 128 B, 16-byte chunks XOR-swizzled
   float4 ra[4], rb[2];
   auto gload = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
-      ra[i] = load_a<PHASE_B>(S, ld, a_row0 + r, a_row_end, k0 + chunk * 4, dinv);
-    }
+#ifdef VOLT_RB_FIRST
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
       rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
     }
+#endif
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      ra[i] = load_a<PHASE_B>(S, ld, a_row0 + r, a_row_end, k0 + chunk * 4, dinv);
+    }
+#ifndef VOLT_RB_FIRST
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
+    }
+#endif
   };
   gload(k_lo);
   for (int kt = 0; kt < nk; ++kt) {
@@ -278,6 +287,157 @@ static __device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int
   tc_fence_after();
   tmem_ld32(c.tmem + lane_base + TM_ACC1 + (uint32_t)(half_id * 32), o);
   tc_fence_before();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "Three CTAs per SM" building blocks (series with T <= 640).  The kernel is latency bound (ncu: issue slots 36 %, L1
+// data pipe ~35 %, tensor pipe 20 % with two resident CTAs), so the lever is more resident CTAs: 128 TMEM columns and
+// ~71 KB of shared memory per CTA instead of 256 / 106 KB.  The price is single-buffered GEMM stages (the MMAs of a
+// k-tile are waited for before the next tile is staged -- the other two CTAs fill the gap) and a two-pass TRSM.
+//   TMEM:  [0,64) accumulator (GEMM result, then the TRSM result, and the parking place of the chunk-0 panel rows
+//          during the diagonal factorisation) | [64,96) A hi | [96,128) A lo
+//   smem:  Y: raw A tile 16 KB | B hi 8 KB | B lo 8 KB  (aliased by LiT | diag scratch and by the store tiles)
+//          Linv operand 32 KB (aliased by the diagonal block D) | vectors
+constexpr uint32_t T3_ACC = 0, T3_HI = 64, T3_LO = 96, T3_COLS = 128;
+constexpr uint32_t Y_BH = A_TILE, Y_BL = A_TILE + B_TILE, Y_BYTES = A_TILE + 2 * B_TILE;   // 32 KB
+constexpr uint32_t Y_LIT = 0, Y_TMP = 64 * CLD * 4;                                         // + 12288 B scratch <= 32 KB
+constexpr uint32_t Y_L_OFF = Y_BYTES, Y_CT_OFF = Y_L_OFF, Y_VEC_OFF = Y_L_OFF + L_BYTES;
+static_assert(Y_TMP + DIAG2_SCRATCH_FLOATS * 4 <= Y_BYTES, "diag scratch must fit the stage region");
+
+template <bool PHASE_B>
+__device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_end, int b_row0, int k_lo, int k_hi, const float* dinv) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int nk = (k_hi - k_lo) / 32;
+  if (nk <= 0) return false;
+  const int row = 32 * (w & 3) + lane, half_id = w >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  uint8_t* RAW = c.X;
+  uint8_t* BH = c.X + Y_BH;
+  uint8_t* BL = c.X + Y_BL;
+  float4 ra[4], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      rb[i] = *reinterpret_cast<const float4*>(S + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      ra[i] = load_a<PHASE_B>(S, ld, a_row0 + r, a_row_end, k0 + chunk * 4, dinv);
+    }
+  };
+  gload(k_lo);
+  for (int kt = 0; kt < nk; ++kt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // the raw tile is not an MMA operand: refill it while the previous MMAs still run
+      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+      *reinterpret_cast<float4*>(RAW + r * 128 + ((chunk ^ (r & 7)) << 4)) = ra[i];
+    }
+    if (kt >= 1) wait_mma(c);       // MMA group kt-1 has consumed the TMEM stage and B hi/lo
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + NT * i;
+      st_split(BH, BL, idx >> 3, idx & 7, rb[i]);
+    }
+    if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
+    __syncthreads();
+    {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = 4 * half_id + q;
+        const float4 v = *reinterpret_cast<const float4*>(RAW + row * 128 + ((chunk ^ (row & 7)) << 4));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hi[4 * q + j] = __float_as_uint(e[j]);
+          lo[4 * q + j] = __float_as_uint(e[j] - __uint_as_float(hi[4 * q + j] & 0xffffe000u));
+        }
+      }
+      tmem_st16(c.tmem + lane_base + T3_HI + (uint32_t)(16 * half_id), hi);
+      tmem_st16(c.tmem + lane_base + T3_LO + (uint32_t)(16 * half_id), lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t dbh = make_desc(s_u32(BH)), dbl = make_desc(s_u32(BL));
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t adv = (uint64_t)(2 * ks);
+        const uint32_t ah = c.tmem + T3_HI + 8 * ks, al = c.tmem + T3_LO + 8 * ks;
+        umma_tf32_ts(c.tmem + T3_ACC, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+        umma_tf32_ts(c.tmem + T3_ACC, ah, dbl + adv, 1u);
+        umma_tf32_ts(c.tmem + T3_ACC, ah, dbh + adv, 1u);
+      }
+      umma_commit(c.bar);
+    }
+  }
+  wait_mma(c);
+  tc_fence_after();
+  return true;
+}
+
+// out = P . Linv^T in two K = 32 passes: the warps holding columns 32 pass .. 32 pass + 31 of P put their hi / lo rows into
+// the 64-column TMEM stage; the result accumulates in T3_ACC (the GEMM result it replaces is already in registers).
+static __device__ void trsm_tc1(Ctx& c, const float (&s)[32], float (&o)[32], int row, int half_id) {
+  const int tid = threadIdx.x, w = tid >> 5;
+  const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  const uint32_t lb = s_u32(c.Lr);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (half_id == pass) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        hi[q] = __float_as_uint(s[q]);
+        lo[q] = __float_as_uint(s[q] - __uint_as_float(hi[q] & 0xffffe000u));
+      }
+      tmem_st32(c.tmem + lane_base + T3_HI, hi);
+      tmem_st32(c.tmem + lane_base + T3_LO, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t adv = (uint64_t)(2 * ks);
+        const uint64_t dbh = make_desc(lb + pass * B_TILE) + adv, dbl = make_desc(lb + (2 + pass) * B_TILE) + adv;
+        const uint32_t ah = c.tmem + T3_HI + 8 * ks, al = c.tmem + T3_LO + 8 * ks;
+        umma_tf32_ts(c.tmem + T3_ACC, al, dbh, (pass == 0 && ks == 0) ? 0u : 1u);
+        umma_tf32_ts(c.tmem + T3_ACC, ah, dbl, 1u);
+        umma_tf32_ts(c.tmem + T3_ACC, ah, dbh, 1u);
+      }
+      umma_commit(c.bar);
+    }
+    wait_mma(c);
+    tc_fence_after();
+  }
+  tmem_ld32(c.tmem + lane_base + T3_ACC + (uint32_t)(half_id * 32), o);
+  tc_fence_before();
+}
+
+// store_block32 with a 32 x 20 float tile per warp (two passes of 16 columns): fits the 32 KB stage region
+__device__ __forceinline__ void store_block32_2p(float* xs, const float (&o)[32], float* gdst, int ld, int lane) {
+#pragma unroll
+  for (int hcol = 0; hcol < 2; ++hcol) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(xs + lane * 20 + 4 * q) =
+          make_float4(o[16 * hcol + 4 * q], o[16 * hcol + 4 * q + 1], o[16 * hcol + 4 * q + 2], o[16 * hcol + 4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (lane >> 2) + 8 * i, ch = (lane & 3) * 4;
+      *reinterpret_cast<float4*>(gdst + (size_t)r * ld + 16 * hcol + ch) = *reinterpret_cast<const float4*>(xs + r * 20 + ch);
+    }
+    __syncwarp();
+  }
 }
 
 // Linv operand (B of the TRSM product): B[n][k] = Linv[n][k] = LiT[k][n], LiT with row stride CLD (floats).
