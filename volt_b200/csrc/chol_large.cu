@@ -299,28 +299,66 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     VOLT_CUDA(cudaFuncSetAttribute(large_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     attr = true;
   }
+  // Look-ahead over two streams.  The deferred K = 256 update of panel P is split by columns: (a) the columns of panel
+  // P+1, on the critical path (stream `st`), and (b) everything to the right of them, which only has to be finished
+  // before the next deferred update touches the same tiles -- it runs on a second stream while panel P+1 (a chain of
+  // 1-CTA diagonal kernels, TRSM panels and narrow updates that idles most of the GPU) is being factored.
+  static cudaStream_t sb = nullptr;
+  static cudaEvent_t ev_panel = nullptr, ev_rest = nullptr, ev_join = nullptr;
+  if (!sb) {
+    VOLT_CUDA(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+    VOLT_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+    VOLT_CUDA(cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming));
+    VOLT_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  constexpr int PB = 4;  // blocks per panel: trailing updates outside the panel are deferred and applied with K = 256
+  auto update = [&](cudaStream_t s2, int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
+    const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
+    if (nrow <= 0 || ncol <= 0) return;
+    dim3 grid(ncol, nrow);
+    large_update_kernel<<<grid, NT, LARGE_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
+  };
+  // deferred update of the panel ending at `panel_end`: part (a) on st after the previous part (b) has left the tiles,
+  // part (b) on sb once the panel is final
+  auto deferred = [&](int mode, int panel_end, bool& rest_pending) -> int {
+    const int next_end = min(p.Tp, panel_end + PB * NB);
+    const int k_lo = panel_end - PB * NB;
+    VOLT_CUDA(cudaEventRecord(ev_panel, st));
+    if (rest_pending) VOLT_CUDA(cudaStreamWaitEvent(st, ev_rest, 0));
+    if (mode == 0) update(st, 0, panel_end, p.Tp, panel_end, next_end, k_lo, panel_end);
+    else update(st, 1, 0, panel_end, panel_end, next_end, k_lo, panel_end);
+    if (next_end < p.Tp) {
+      VOLT_CUDA(cudaStreamWaitEvent(sb, ev_panel, 0));
+      if (mode == 0) update(sb, 0, next_end, p.Tp, next_end, p.Tp, k_lo, panel_end);
+      else update(sb, 1, 0, panel_end, next_end, p.Tp, k_lo, panel_end);
+      VOLT_CUDA(cudaEventRecord(ev_rest, sb));
+      rest_pending = true;
+    }
+    return VOLT_OK;
+  };
+  auto join = [&](bool& rest_pending) -> int {
+    if (rest_pending) VOLT_CUDA(cudaStreamWaitEvent(st, ev_rest, 0));
+    rest_pending = false;
+    return VOLT_OK;
+  };
   float jit_used = 0.f;
   for (int attempt = 0;; ++attempt) {
     p.dadd = dadd0 + jit_used;
     VOLT_CUDA(cudaMemsetAsync(p.Ut, 0, tp2 * sizeof(float), st));
     large_build_kernel<<<p.Tp, 256, 0, st>>>(p);
-    constexpr int PB = 4;  // blocks per panel: trailing updates outside the panel are deferred and applied with K = 256
-    auto update = [&](int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
-      const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
-      if (nrow <= 0 || ncol <= 0) return;
-      dim3 grid(ncol, nrow);
-      large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
-    };
+    bool rest_pending = false;
     for (int j = 0; j < p.nb; ++j) {
       const int R0 = j * NB, panel_end = min(p.Tp, (j / PB + 1) * PB * NB);
       large_diag_kernel<<<1, NT, LARGE_SMEM, st>>>(p, j);
       const int rows = p.Tp - (R0 + NB);
       if (rows > 0) {
         large_panel_kernel<<<(rows + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, j, 0);
-        update(0, R0 + NB, p.Tp, R0 + NB, panel_end, R0, R0 + NB);                  // inside the panel, K = 64
-        if (R0 + NB == panel_end) update(0, panel_end, p.Tp, panel_end, p.Tp, panel_end - PB * NB, panel_end);  // K = 256
+        update(st, 0, R0 + NB, p.Tp, R0 + NB, panel_end, R0, R0 + NB);                  // inside the panel, K = 64
+        if (R0 + NB == panel_end) { s = deferred(0, panel_end, rest_pending); if (s) return s; }
       }
     }
+    s = join(rest_pending);
+    if (s) return s;
     int flag = -1;
     VOLT_CUDA(cudaMemcpyAsync(&flag, p.flag, 4, cudaMemcpyDeviceToHost, st));
     VOLT_CUDA(cudaStreamSynchronize(st));
@@ -328,19 +366,15 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     jit_used = mp.jitter * powf(10.f, (float)attempt);
   }
   if (mp.do_inverse) {
-    constexpr int PB = 4;
-    auto update = [&](int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
-      const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
-      if (nrow <= 0 || ncol <= 0) return;
-      dim3 grid(ncol, nrow);
-      large_update_kernel<<<grid, NT, LARGE_SMEM, st>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
-    };
+    bool rest_pending = false;
     for (int k = 0; k < p.nb; ++k) {
       const int R0 = k * NB, rows_done = R0 + NB, panel_end = min(p.Tp, (k / PB + 1) * PB * NB);
       large_panel_kernel<<<(rows_done + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, k, 1);
-      update(1, 0, rows_done, rows_done, panel_end, R0, rows_done);                 // columns inside the panel, K = 64
-      if (rows_done == panel_end) update(1, 0, panel_end, panel_end, p.Tp, panel_end - PB * NB, panel_end);  // K = 256
+      update(st, 1, 0, rows_done, rows_done, panel_end, R0, rows_done);                 // columns inside the panel, K = 64
+      if (rows_done == panel_end && panel_end < p.Tp) { s = deferred(1, panel_end, rest_pending); if (s) return s; }
     }
+    s = join(rest_pending);
+    if (s) return s;
   }
   large_finish_kernel<<<1, 256, 0, st>>>(p, jit_used, mp.scalars + (size_t)b * NSCALARS,
                                          (mp.alpha && mp.do_inverse) ? mp.alpha + (size_t)b * mp.T : nullptr,

@@ -115,7 +115,13 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   const bool ma = p.mean_kind != MA_GIVEN;
   const bool need_ee = (p.mean_kind == MA_DEWMA || p.mean_kind == MA_TEWMA);
   const bool need_e = need_ee || p.mean_kind == MA_MEANREVERT;
-  float* t_pv = eetail + (k + 1);       // TS*Hp
+  // train-part prefixes of the MA windows, one per horizon step (identical for every draw of the series): the window sum
+  // of step idx starts with the k - idx terms that come from the training tail, so that part of the fma chain is
+  // computed once per CTA and every draw only continues it over its own idx generated values (same summation order)
+  float* Pm = eetail + (k + 1);         // Hp
+  float* Pe = Pm + Hp;                  // Hp
+  float* Pee = Pe + Hp;                 // Hp
+  float* t_pv = Pee + Hp;               // TS*Hp
   float* t_out = t_pv + TS * Hp;
   float* nxt = t_out + TS * Hp;
   float* t_eps = nxt;                   // base normals (absent with in-kernel Philox)
@@ -151,6 +157,26 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   const float y_first = yb[0];
   const float e_first = ma ? p.e_train[(size_t)b * (n + 1)] : 0.f;
   const float ee_first = need_ee ? p.ee_train[(size_t)b * (n + 1)] : 0.f;
+  if (ma && !p.joint) {
+    for (int idx = tid; idx < H; idx += TS) {
+      const int m = n + idx;
+      const int tc = min(k, max(0, k - idx));        // window terms with absolute index < n      (training y)
+      float acc = 0.f;
+      for (int t = 0; t < tc; ++t) acc = fmaf(sw[t], grown_at(m - k + t, n, ytail, tly, y_first, nullptr), acc);
+      Pm[idx] = acc;
+      if (need_ee) {
+        const int tc1 = min(k, max(0, k - idx + 1)); // window terms with absolute index < n + 1  (training e / ee)
+        float a1 = 0.f, a2 = 0.f;
+        for (int t = 0; t < tc1; ++t) {
+          a1 = fmaf(sw[t], grown_at(m - k + t, n + 1, etail, tl, e_first, nullptr), a1);
+          a2 = fmaf(sw[t], grown_at(m - k + t, n + 1, eetail, tl, ee_first, nullptr), a2);
+        }
+        Pe[idx] = a1;
+        Pee[idx] = a2;
+      }
+    }
+    __syncthreads();
+  }
   const float* ser = p.series + (size_t)b * NSERIES;
   const float c0 = ser[0], uz = ser[1], Vn1 = ser[2], dx = ser[3], jit_s = ser[4];
   const float latent = (p.use_theta && p.latent) ? p.latent[b] : 0.f;
@@ -194,8 +220,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
         // ---- test mean = last element of the MA path over the grown series (EWMA.py:48-50 and twins)
         float m_test;
         if (ma) {
-          float e_m = 0.f;
-          for (int t = 0; t < k; ++t) e_m = fmaf(sw[t], grown_at(m - k + t, n, ytail, tly, y_first, out), e_m);
+          float e_m = Pm[idx];   // window y[m-k .. m-1]: training part above, then the draw's own samples out[idx-k+t]
+          for (int t = max(0, k - idx); t < k; ++t) e_m = fmaf(sw[t], out[idx - k + t], e_m);
           m_test = e_m;
           if (p.mean_kind == MA_MEANREVERT) {
             if (m >= 1) {
@@ -203,13 +229,13 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
               m_test = e_m - p.mr_theta * (e_prev - mr_lat);
             }
           } else if (need_ee) {
-            float ee_m = 0.f;  // window e[m-k .. m-1]
-            for (int t = 0; t < k; ++t) ee_m = fmaf(sw[t], grown_at(m - k + t, n + 1, etail, tl, e_first, eh), ee_m);
+            float ee_m = Pe[idx];  // window e[m-k .. m-1]; generated part eh[idx-k+t-1]
+            for (int t = max(0, k - idx + 1); t < k; ++t) ee_m = fmaf(sw[t], eh[idx - k + t - 1], ee_m);
             if (p.mean_kind == MA_DEWMA) {
               m_test = 2.f * e_m - ee_m;
             } else {
-              float eee_m = 0.f;  // window ee[m-k .. m-1]
-              for (int t = 0; t < k; ++t) eee_m = fmaf(sw[t], grown_at(m - k + t, n + 1, eetail, tl, ee_first, eeh), eee_m);
+              float eee_m = Pee[idx];  // window ee[m-k .. m-1]; generated part eeh[idx-k+t-1]
+              for (int t = max(0, k - idx + 1); t < k; ++t) eee_m = fmaf(sw[t], eeh[idx - k + t - 1], eee_m);
               m_test = 3.f * e_m - 3.f * ee_m + eee_m;
             }
             if (idx >= 1) eeh[idx - 1] = ee_m;  // ee[n+idx]
@@ -305,7 +331,7 @@ int launch_rollout(RolloutParams p, cudaStream_t st) {
   const bool need_ee = (p.mean_kind == MA_DEWMA || p.mean_kind == MA_TEWMA);
   const bool need_e = need_ee || p.mean_kind == MA_MEANREVERT;
   const int ntiles = 2 + (p.eps ? 1 : 0) + (need_e ? 1 : 0) + (need_ee ? 1 : 0);
-  auto smem_for = [&](int ts) { return sizeof(float) * ((size_t)4 * p.k + 2 + (size_t)ntiles * ts * p.Hp); };
+  auto smem_for = [&](int ts) { return sizeof(float) * ((size_t)4 * p.k + 2 + 3 * (size_t)p.Hp + (size_t)ntiles * ts * p.Hp); };
   while (TS > 32 && smem_for(TS) > 56 * 1024) TS >>= 1;   // aim for >= 4 resident CTAs per SM
   const size_t smem = smem_for(TS);
   if (smem > 220 * 1024) {
