@@ -159,6 +159,17 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
                  const float* resid_given, const float* mean_test, int use_theta, float theta, const float* latent, int joint,
                  float jitter, unsigned long long seed, float* samples, int* draw_info, int* series_info, void* stream);
 
+/* Forecast evaluation reductions over a rollout tensor, one pass over samples (B,S,H):
+ *   ecdf[b,h]   = #{s : v < truth[b,h]} / S      voltron/option_utils.py:48-52 (ECDF; the caller passes log prices and the
+ *                                                 log of the realised price) and the weather calibration notebook's
+ *                                                 ECDF(sample, truth) = sum(sample < truth, 0) / S (calib_plotter cell 2)
+ *   mean, sd    = samples.mean(0), samples.std(0) (unbiased), nll = -Normal(mean, sd).log_prob(truth)   (cell 15, GetNLL)
+ *   payoff[b,h] = mean_s max(v - strike[b,h], 0)  voltron/option_utils.py:37 (Pricer's Monte-Carlo call valuation)
+ * with v = samples[b,s,h], or exp(samples[b,s,h]) when exp_flag != 0 (the notebooks' exp=True).  truth / strike are (B,H)
+ * or NULL; every output is (B,H) or NULL (nll needs truth, payoff needs strike). */
+int volt_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag,
+                       float* ecdf, float* mean, float* sd, float* nll, float* payoff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

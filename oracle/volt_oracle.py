@@ -334,6 +334,34 @@ def rollout_closed_form(train_x, train_y, log_vol_path, test_x, pred_vol, eps, k
 
 
 # =============================================================================== training loops
+# =============================================================================== evaluation reductions (section 8f-3)
+def ecdf_logpx(sample_pxs, true_px):
+    """voltron/option_utils.py:48-52 -- fraction of sampled prices whose log lies below the log of the realised price."""
+    smp = sample_pxs.log().sort()[0]
+    log_px = true_px.log()
+    return (torch.sum(smp < log_px) / smp.shape[0]).item()
+
+
+def call_valuation(mc_pxs, strike):
+    """voltron/option_utils.py:37 -- np.mean(np.maximum(mc_pxs[:, e] - K, 0)) for one expiry column (numpy: fp32 mean)."""
+    return torch.clamp(mc_pxs - strike, min=0).mean(0)
+
+
+def rollout_stats(samples, truth=None, strike=None, exp=False):
+    """Per (series, step) reductions over samples (B,S,H).  ecdf: calib_plotter notebook cell 2
+    (`torch.sum(sample < truth, 0) / S`); nll: cell 15 (`-Normal(preds.mean(0), preds.std(0)).log_prob(truth)`);
+    payoff: option_utils.py:37.  exp=True applies the notebooks' `preds = preds.exp()` first.  [notebook code is restated,
+    it cannot be imported: unpinned, but it is three torch calls]"""
+    v = samples.exp() if exp else samples
+    out = dict(mean=v.mean(1), std=v.std(1))
+    if truth is not None:
+        out["ecdf"] = torch.sum(v < truth.unsqueeze(1), 1) / v.shape[1]
+        out["nll"] = -torch.distributions.Normal(out["mean"], out["std"]).log_prob(truth)
+    if strike is not None:
+        out["payoff"] = torch.clamp(v - strike.unsqueeze(1), min=0).mean(1)
+    return out
+
+
 def _adam_loop(params, closure, iters, lr):
     opt = torch.optim.Adam(params, lr=lr)
     trace = []

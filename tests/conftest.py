@@ -27,3 +27,8 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     return torch.load(os.path.join(ROOT, "tests", "golden", "volt_golden.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def eval_golden():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "eval_golden.pt"), weights_only=False)

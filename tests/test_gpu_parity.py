@@ -522,3 +522,69 @@ def test_rollout_singular_training_block_takes_jitter(vb):
     finally:
         O.psd_safe_cholesky = orig
     assert relerr(out[0], want) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ evaluation reductions
+def test_ecdf_and_pricer_goldens(vb, eval_golden):
+    """voltron.option_utils.ECDF and the two Pricer reductions against values produced by the reference's own file."""
+    import voltron
+
+    for c in eval_golden["ecdf"]:
+        assert voltron.option_utils.ECDF(c["sample_pxs"], c["true_px"]) == pytest.approx(c["ecdf"], abs=1e-7)
+    g = eval_golden["pricer"]
+    E = g["mc_pxs"].shape[1]
+    for K in g["strikes"].unique():
+        val = voltron.option_utils.CallValuation(g["mc_pxs"], float(K))
+        assert val.shape == (E,)
+        for i in range(g["strikes"].numel()):
+            if float(g["strikes"][i]) == float(K):
+                e = int(g["expiry_idx"][i])
+                assert float(val[e]) == pytest.approx(float(g["valuation"][i]), rel=1e-6)
+                assert voltron.option_utils.ECDF(g["mc_pxs"][:, e], g["true_pxs"][e]) == pytest.approx(float(g["percentile"][i]), abs=1e-7)
+
+
+@pytest.mark.parametrize("B,S,H,exp", [(1, 1, 1, False), (3, 50, 7, True), (2, 257, 30, False), (5, 64, 33, True), (2, 1000, 70, False)])
+def test_rollout_stats_vs_oracle(vb, B, S, H, exp):
+    g = torch.Generator().manual_seed(B * 1000 + S + H)
+    smp = 2.0 + 0.3 * torch.randn(B, S, H, generator=g)
+    truth = 2.0 + 0.3 * torch.randn(B, H, generator=g)
+    if exp:
+        truth = truth.exp()
+    strike = truth * 0.97
+    got = vb.ops.rollout_stats(smp, truth=truth, strike=strike, exp=exp)
+    if S == 1:
+        # a single draw has no sample std: torch's Normal rejects the NaN scale (the notebook's try/except skips the case);
+        # the kernel reports NaN for std and nll and the well-defined quantities as usual
+        with pytest.raises(ValueError), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            O.rollout_stats(smp.double(), truth=truth.double(), strike=strike.double(), exp=exp)
+        assert torch.isnan(got["std"]).all() and torch.isnan(got["nll"]).all()
+        assert relerr(got["mean"], smp[:, 0]) < 1e-6
+        assert float((got["ecdf"].cpu() - (smp[:, 0] < truth).float()).abs().max()) == 0.0
+        return
+    want = O.rollout_stats(smp.double(), truth=truth.double(), strike=strike.double(), exp=exp)
+    # counts are integers: exact unless a sample sits within fp32 rounding of the threshold (exp path: expf vs exp)
+    assert float((got["ecdf"].cpu().double() - want["ecdf"]).abs().max()) <= (1.0 / S if exp else 0.0) + 1e-7
+    assert relerr(got["mean"], want["mean"]) < 1e-6
+    assert relerr(got["payoff"], want["payoff"]) < 1e-5
+    assert relerr(got["std"], want["std"]) < 1e-5
+    torch.testing.assert_close(got["nll"].cpu().double(), want["nll"], rtol=1e-4, atol=1e-5)
+
+
+def test_rollout_stats_full_size_properties(vb):
+    """c4 per-GPU share shape (512 x 512 x 30): ECDF is monotone in the threshold and mean/std match torch on the device."""
+    g = torch.Generator().manual_seed(11)
+    smp = torch.randn(512, 512, 30, generator=g).cuda()
+    t0 = torch.zeros(512, 30).cuda()
+    lo = vb.ops.rollout_stats(smp, truth=t0 - 0.5)["ecdf"]
+    hi = vb.ops.rollout_stats(smp, truth=t0 + 0.5)
+    assert bool((lo <= hi["ecdf"]).all())
+    assert relerr(hi["std"], smp.std(1)) < 1e-5
+    torch.testing.assert_close(hi["mean"], smp.mean(1), rtol=1e-4, atol=1e-6)
+    assert float((hi["ecdf"] - (smp < 0.5).float().mean(1)).abs().max()) == 0.0
+
+
+def test_rollout_stats_arg_errors(vb):
+    lib = vb._lib.load()
+    assert lib.volt_rollout_stats(None, 1, 1, 1, None, None, 0, None, None, None, None, None, None) != 0
+    assert b"null samples" in lib.volt_last_error()

@@ -218,3 +218,29 @@ def test_synth_series_shapes():
     assert torch.all(vol > 0) and abs(float(logy[0, 0]) - math.log(10.0)) < 1e-6
     x2, vol2, _ = O.synth_series(3, 64)
     assert torch.equal(vol, vol2)
+
+
+# ------------------------------------------------------------------ evaluation reductions (section 8f-3)
+def test_golden_ecdf(eval_golden):
+    for c in eval_golden["ecdf"]:
+        assert O.ecdf_logpx(c["sample_pxs"], c["true_px"]) == c["ecdf"]
+
+
+def test_golden_pricer_reductions(eval_golden):
+    g = eval_golden["pricer"]
+    for i in range(g["strikes"].numel()):
+        e = int(g["expiry_idx"][i])
+        val = O.call_valuation(g["mc_pxs"][:, e], g["strikes"][i])
+        assert abs(float(val) - float(g["valuation"][i])) <= 1e-6 * max(1.0, abs(float(g["valuation"][i])))
+        assert O.ecdf_logpx(g["mc_pxs"][:, e], g["true_pxs"][e]) == pytest.approx(float(g["percentile"][i]), abs=1e-7)
+
+
+def test_rollout_stats_oracle_consistency():
+    g = torch.Generator().manual_seed(3)
+    smp = 2.0 + 0.3 * torch.randn(3, 50, 7, generator=g)
+    truth = 2.0 + 0.3 * torch.randn(3, 7, generator=g)
+    st = O.rollout_stats(smp, truth=truth.exp(), strike=truth.exp(), exp=True)   # exp=True: truth / strike in price space
+    assert st["ecdf"].shape == (3, 7) and float(st["ecdf"].min()) >= 0.0 and float(st["ecdf"].max()) <= 1.0
+    # the notebook's per-column ECDF equals the option_utils one on positive prices
+    assert float(st["ecdf"][1, 2]) == pytest.approx(O.ecdf_logpx(smp[1, :, 2].exp(), truth[1, 2].exp()), abs=1e-7)
+    assert torch.isfinite(O.rollout_stats(smp, truth=truth)["nll"]).all()

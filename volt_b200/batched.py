@@ -89,6 +89,13 @@ def rollouts(x, logy, vol, pred_vol, eps=None, k=25, mean_func="ewma", theta=Non
     return out, dinfo, sinfo
 
 
+def rollout_stats(samples, truth=None, strike=None, exp=False):
+    """Per-series, per-step evaluation of a (B,S,H) rollout tensor without leaving the GPU: sample percentile of the
+    realised value (ECDF), moment-matched Gaussian NLL, mean / std and Monte-Carlo call payoff (ops.rollout_stats).
+    Series-sharded callers pass their local block; no collective is involved."""
+    return ops.rollout_stats(samples, truth=truth, strike=strike, exp=exp)
+
+
 def synth_series(B, T, dt=1.0 / 252, seed=2019, start=0):
     """Synthetic workload of SURVEY.md section 8d (same generator as oracle.volt_oracle.synth_series, restated so the
     product never imports the oracle): vol = exp(BM) with V0 = 0.2, alpha = 1.25; log price a GBM from log 10.

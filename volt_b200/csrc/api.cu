@@ -474,4 +474,14 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
   return launch_rollout(q, st);
 }
 
+int volt_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag,
+                       float* ecdf, float* mean, float* sd, float* nll, float* payoff, void* stream) {
+  VOLT_REQUIRE(samples, "volt_rollout_stats: null samples");
+  VOLT_REQUIRE(B >= 1 && S >= 1 && H >= 1, "volt_rollout_stats: need B, S, H >= 1 (got %d, %d, %d)", B, S, H);
+  VOLT_REQUIRE(!nll || truth, "volt_rollout_stats: nll needs truth");
+  VOLT_REQUIRE(!payoff || strike, "volt_rollout_stats: payoff needs strike");
+  VOLT_REQUIRE(!ecdf || truth, "volt_rollout_stats: ecdf needs truth");
+  return launch_rollout_stats(samples, B, S, H, truth, strike, exp_flag, ecdf, mean, sd, nll, payoff, ST(stream));
+}
+
 }  // extern "C"

@@ -56,6 +56,8 @@ int launch_mll_batched_simt(MllParams p, cudaStream_t st); // fp32 CUDA-core GEM
 int launch_mll_batched_tc(MllParams p, cudaStream_t st);   // tcgen05 3xTF32 tensor-core products (chol_tc.cu)
 int launch_mll_large(const MllParams& p, int b, cudaStream_t st);  // multi-CTA path for one long series (chol_large.cu)
 int launch_rollout(RolloutParams p, cudaStream_t st);
+int launch_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag, float* ecdf,
+                         float* mean, float* sd, float* nll, float* payoff, cudaStream_t st);
 int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kind, float theta, const float* latent, float* out,
                     float* e_out, float* ee_out, float* resid_out, cudaStream_t st);
 int launch_cumtrapz(const float* x, int x_batched, const float* vol, int B, int T, int mode, int half_last, float* V,

@@ -358,3 +358,40 @@ def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0
         if bool((dinfo & 5).any()):
             raise NotPSDError("rollout: a conditional covariance was not positive definite after jitter retries")
     return out, dinfo, sinfo
+
+
+def rollout_stats(samples, truth=None, strike=None, exp=False):
+    """Evaluation reductions over a rollout tensor in one pass.
+
+    samples (B,S,H) or (S,H); truth / strike (B,H), (H,) or None.  Returns a dict of (B,H) CUDA tensors:
+    `mean`, `std` (unbiased, torch.std), and when truth is given `ecdf` = sum(v < truth, 0) / S
+    (voltron/option_utils.py:48-52; weather calibration notebook cell 2) and `nll` = -Normal(mean, std).log_prob(truth)
+    (notebook cell 15); when strike is given `payoff` = mean(max(v - strike, 0)) (option_utils.py:37).
+    exp=True evaluates v = exp(sample) (the notebooks' exp=True: samples are log values)."""
+    dev = _dev()
+    sm = _f32(samples, dev)
+    if sm.dim() == 2:
+        sm = sm.unsqueeze(0)
+    B, S, H = sm.shape
+    sm = sm.contiguous()
+
+    def bh(t):
+        if t is None:
+            return None
+        t = _f32(t, dev)
+        if t.dim() == 0:
+            t = t.reshape(1, 1)
+        return t.reshape(-1, t.shape[-1]).expand(B, H).contiguous()
+
+    tr, st = bh(truth), bh(strike)
+    out = {"mean": _empty((B, H), dev), "std": _empty((B, H), dev)}
+    if tr is not None:
+        out["ecdf"] = _empty((B, H), dev)
+        out["nll"] = _empty((B, H), dev)
+    if st is not None:
+        out["payoff"] = _empty((B, H), dev)
+    _lib.check(_lib.load().volt_rollout_stats(_ptr(sm), B, S, H, _ptr(tr), _ptr(st), int(bool(exp)), _ptr(out.get("ecdf")),
+                                              _ptr(out["mean"]), _ptr(out["std"]), _ptr(out.get("nll")), _ptr(out.get("payoff")),
+                                              _stream()), "volt_rollout_stats")
+    return out
+
