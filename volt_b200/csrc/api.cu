@@ -298,7 +298,7 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   void* vres = nullptr;
   s = get_workspace(bt * sizeof(float), &vres, 1);   // reserve the prefix-sum buffer at full size (no regrow mid-pipeline)
   if (s) return s;
-  const int slots = 2 * sm_count();
+  const int slots = mll_tc_resident_ctas(T, 0);
   const int B0 = (B >= 2 * slots) ? slots : B;
   const size_t n0 = (size_t)B0 * T;
   VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, s_copy));

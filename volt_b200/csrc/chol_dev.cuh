@@ -203,6 +203,7 @@ __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, 
     }
     y[c] = (acc0 + acc1) * inv;
   }
+  __syncwarp();   // both half-warps have read their (duplicate) rows of D before the write-back below
   if (lane < 16) {
     float dl = 0.f;
 #pragma unroll

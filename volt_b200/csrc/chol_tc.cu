@@ -378,6 +378,17 @@ static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   return check_cuda(cudaGetLastError(), "mll_batched_tc_kernel");
 }
 
+// resident CTAs (= series in flight) of the batched kernel for series of length T: the first wave of a batch
+int mll_tc_resident_ctas(int T, int two_rhs) {
+  const int Tp = (T + NB - 1) / NB * NB;
+  const size_t vec = sizeof(float) * (size_t)((two_rhs ? 4 : 3) * Tp + NB + 2 * NB + 32 + 12);
+  const size_t smem3 = tc::Y_VEC_OFF + vec;
+  if (3 * (smem3 + 1024) <= 233472) return 3 * sm_count();
+  const size_t smem = tc::VEC_OFF + vec;
+  int per_sm = (int)(233472 / (smem + 1024));
+  return sm_count() * (per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm));
+}
+
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.Tp = (p.T + NB - 1) / NB * NB;
   p.nb = p.Tp / NB;

@@ -54,6 +54,7 @@ struct RolloutParams {
 int launch_mll_batched(MllParams p, cudaStream_t st);      // dispatches on the selected implementation
 int launch_mll_batched_simt(MllParams p, cudaStream_t st); // fp32 CUDA-core GEMM micro-kernel (chol_batched.cu)
 int launch_mll_batched_tc(MllParams p, cudaStream_t st);   // tcgen05 3xTF32 tensor-core products (chol_tc.cu)
+int mll_tc_resident_ctas(int T, int two_rhs);              // series in flight per launch of that kernel
 int launch_mll_large(const MllParams& p, int b, cudaStream_t st);  // multi-CTA path for one long series (chol_large.cu)
 int launch_rollout(RolloutParams p, cudaStream_t st);
 int launch_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag, float* ecdf,
