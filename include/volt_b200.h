@@ -170,6 +170,23 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
 int volt_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag,
                        float* ecdf, float* mean, float* sd, float* nll, float* payoff, void* stream);
 
+/* GPCV stage (LearnGPCV, voltron/train_utils.py:15-67): per-row terms of the variational ELBO
+ * and the gradient of the Cholesky variational factor, for B series of n points.
+ *   chol_var (B,n,n): CholeskyVariationalDistribution parameter, lower triangle used (single_task_variational_gp.py:86-88)
+ *   W        (B,n,n): K^-1 tril(chol_var), K = BM kernel + 1e-3 I (prior of the UnwhitenedVariationalStrategy)
+ *   var_mean, y (B,n): variational mean and the scaled returns (train_utils.py:16-18)
+ *   gh_t, gh_w (nq <= 128): Gauss-Hermite nodes / weights (train_utils.py:52 uses 75)
+ * grad_chol (B,n,n) = d(-ELBO)/d chol_var with ELBO scaled by inv_n = 1/n (VariationalELBO, train_utils.py:46);
+ * rows (B,n,6) = E_q[log p(y_i|f_i)], its derivative in the variational mean, sum_k L[i,k] W[i,k], sum_k W[i,k]^2,
+ * log|L[i,i]|, S_ii -- the host layer sums them into the loss and the gradients of the mean / kernel parameters. */
+int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t,
+                   const float* gh_w, int nq, int B, int n, float inv_n, float* grad_chol, float* rows, void* stream);
+
+/* One torch.optim.Adam step (no weight decay / amsgrad) over a flat parameter buffer: the optimiser of every training
+ * loop of the reference (train_utils.py:38-41 lr 0.01; :76-78, :123-125, :236-238 lr 0.01).  step counts from 1. */
+int volt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
+                   float beta2, float eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

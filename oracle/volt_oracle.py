@@ -334,6 +334,108 @@ def rollout_closed_form(train_x, train_y, log_vol_path, test_x, pred_vol, eps, k
 
 
 # =============================================================================== training loops
+# =============================================================================== GPCV (section 8f-1)
+# LearnGPCV (voltron/train_utils.py:15-67): a variational GP on the log-volatility f with inducing points = training
+# inputs, UnwhitenedVariationalStrategy + CholeskyVariationalDistribution (models/single_task_variational_gp.py:86-107),
+# BMKernel prior with ConstantMean, the "exp" VolatilityGaussianLikelihood (likelihoods/volatility_likelihood.py:44-52)
+# and the 75-point Gauss-Hermite VariationalELBO.  [GPyTorch slice restated from memory of 1.6-1.8: PARITY UNPINNED]
+#   * training-mode call with x == inducing points returns q(u) = N(m, L_S L_S^T) itself (UnwhitenedVariationalStrategy.forward)
+#   * prior p(u) = N(c 1, K + 1e-3 I)  (prior_distribution: lazy_covariance_matrix.add_jitter(), default 1e-3)
+#   * KL(q || p) = 0.5 [logdet K - logdet S + tr(K^-1 S) + (c - m)^T K^-1 (c - m) - n]   (kl_mvn_mvn, Cholesky branch)
+#   * ELBO = (sum_i E_q[log p(y_i | f_i)] - KL) / n  (VariationalELBO, num_data = n, combine_terms=True)
+#   * E_q[.] by GaussHermiteQuadrature1D: f = sqrt(2 S_ii) t_k + m_i, (1/sqrt(pi)) sum_k w_k log p(y_i | f)
+GPCV_PRIOR_JITTER = 1e-3
+
+
+def gauss_hermite(n=75, dtype=torch.float32):
+    import numpy as np
+
+    t, w = np.polynomial.hermite.hermgauss(n)
+    return torch.as_tensor(t, dtype=dtype), torch.as_tensor(w, dtype=dtype)
+
+
+def gpcv_scaled_returns(train_x, train_y):
+    """train_utils.py:16-18."""
+    dt = train_x[1] - train_x[0]
+    return (train_y[1:] - train_y[:-1]) / (train_y[:-1]) / (dt ** 0.5)
+
+
+def gpcv_loglik_exp(f, y):
+    """volatility_likelihood.py:50-52 with param="exp": Normal(0, exp(f).clamp(min=1e-3)).log_prob(y)."""
+    scale = f.exp().clamp(min=1e-3)
+    return -scale.log() - 0.5 * LOG_2PI - 0.5 * (y / scale) ** 2
+
+
+def gpcv_neg_elbo(x, y, var_mean, chol_var, raw_vol, constant, nq=75):
+    """-VariationalELBO for one series (train_utils.py:44-56).  chol_var is the full (n,n) parameter; its lower triangle is
+    used (CholeskyVariationalDistribution.forward masks it)."""
+    n = x.numel()
+    Ls = torch.tril(chol_var)
+    vol = torch.sigmoid(raw_vol)                       # Interval(0,1) (BMKernel.py:10)
+    K = vol * torch.minimum(x.view(-1, 1), x.view(1, -1)) + GPCV_PRIOR_JITTER * torch.eye(n, dtype=x.dtype)
+    Lk = torch.linalg.cholesky(K)
+    d = (constant - var_mean).unsqueeze(-1)
+    A1 = torch.linalg.solve_triangular(Lk, torch.cat((d, Ls), -1), upper=False)
+    logdet_k = 2.0 * torch.log(torch.diagonal(Lk)).sum()
+    logdet_s = 2.0 * torch.log(torch.diagonal(Ls).abs()).sum()
+    kl = 0.5 * (logdet_k - logdet_s + (A1 ** 2).sum() - n)
+    t, w = gauss_hermite(nq, x.dtype)
+    s_diag = (Ls ** 2).sum(-1)
+    f = (2.0 * s_diag).sqrt().unsqueeze(-1) * t + var_mean.unsqueeze(-1)        # (n, nq)
+    e = (gpcv_loglik_exp(f, y.unsqueeze(-1)) * w).sum(-1) / math.sqrt(math.pi)
+    return -(e.sum() - kl) / n
+
+
+def gpcv_init(x, y):
+    """SingleTaskVariationalGP.initialize_variational_parameters with param="exp" (single_task_variational_gp.py:204-253)
+    at the default BMKernel (vol = 0.2).  Returns (variational_mean, chol_variational_covar)."""
+    n = y.shape[0]
+    running_std = torch.stack([y[:i].std(0) for i in range(n)])
+    running_std[:10] = running_std[10]
+    f = running_std.clamp(min=1e-4).log()
+    inverse_hessian = torch.diag_embed(0.5 * y.pow(-2.0) * (f * 2.0).exp()).clamp(min=1e-4, max=1000.0)
+    kuu = 0.2 * torch.minimum(x.view(-1, 1), x.view(1, -1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kuu_chol = psd_safe_cholesky(kuu)               # LazyTensor.cholesky() -> psd_safe_cholesky (x[0] = 0 => singular)
+    inner = kuu_chol.t() @ inverse_hessian @ kuu_chol + torch.eye(n, dtype=x.dtype)       # add_jitter(1.0)
+    S = kuu_chol @ torch.linalg.solve(inner, kuu_chol.t())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S_root = torch.tril(psd_safe_cholesky(S)) * 10.0  # root_decomposition(method="cholesky").root.evaluate().tril() * 10
+    return f, S_root
+
+
+def learn_gpcv(train_x, train_y, train_iters=1000, eps=None, return_state=False):
+    """LearnGPCV (train_utils.py:15-67).  eps (n, 10): the base normals of the final `likelihood(predictive)` marginal
+    (Likelihood.marginal draws settings.num_likelihood_samples = 10 function samples: mean + L_S eps)."""
+    x = train_x.reshape(-1)
+    y = gpcv_scaled_returns(x, train_y)
+    f0, s_root = gpcv_init(x, y)
+    vm = f0.clone().requires_grad_(True)
+    cv = s_root.clone().requires_grad_(True)
+    raw_vol = torch.logit(torch.tensor([0.2], dtype=x.dtype)).requires_grad_(True)       # BMKernel(vol=0.2)
+    const = torch.zeros(1, dtype=x.dtype, requires_grad=True)                               # ConstantMean init
+    # model.parameters() order: variational_mean, chol_variational_covar, mean_module.constant, covar_module.raw_vol
+    opt = torch.optim.Adam([vm, cv, const, raw_vol], lr=0.01)
+    losses = []
+    for _ in range(train_iters):
+        opt.zero_grad()
+        loss = gpcv_neg_elbo(x, y, vm, cv, raw_vol, const)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    with torch.no_grad():
+        if eps is None:
+            eps = torch.randn(x.numel(), 10, dtype=x.dtype)
+        fs = (torch.tril(cv) @ eps).t() + vm                 # MultivariateNormal.rsample((10,))
+        pred_scale = fs.exp().clamp(min=1e-3).mean(0)        # likelihood(...).scale.mean(0)
+    if return_state:
+        return pred_scale, dict(var_mean=vm.detach(), chol_var=cv.detach(), raw_vol=raw_vol.detach(), constant=const.detach(),
+                                losses=losses, y=y)
+    return pred_scale
+
+
 # =============================================================================== evaluation reductions (section 8f-3)
 def ecdf_logpx(sample_pxs, true_px):
     """voltron/option_utils.py:48-52 -- fraction of sampled prices whose log lies below the log of the realised price."""

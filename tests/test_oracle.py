@@ -1,6 +1,7 @@
 """Pin the CPU oracle: (1) against golden vectors produced by the reference's own files
 (tests/golden/make_golden.py), (2) against closed-form known-answer tests KAT-1..5."""
 import math
+import warnings
 
 import pytest
 import torch
@@ -244,3 +245,56 @@ def test_rollout_stats_oracle_consistency():
     # the notebook's per-column ECDF equals the option_utils one on positive prices
     assert float(st["ecdf"][1, 2]) == pytest.approx(O.ecdf_logpx(smp[1, :, 2].exp(), truth[1, 2].exp()), abs=1e-7)
     assert torch.isfinite(O.rollout_stats(smp, truth=truth)["nll"]).all()
+
+
+# ------------------------------------------------------------------ GPCV (section 8f-1)
+def test_gpcv_analytic_gradients_match_autograd():
+    """The closed-form gradients the GPU path uses (volt_b200/gpcv.py, gpcv.cu) against autograd of the oracle ELBO, fp64."""
+    torch.manual_seed(0)
+    n = 24
+    x = torch.arange(n, dtype=torch.float64) / 252
+    y = torch.randn(n, dtype=torch.float64) * 0.3
+    vm = (torch.randn(n, dtype=torch.float64) * 0.2 - 1.5).requires_grad_(True)
+    cv = (torch.tril(torch.randn(n, n, dtype=torch.float64)) * 0.05 + 0.3 * torch.eye(n, dtype=torch.float64)).requires_grad_(True)
+    raw_vol = torch.tensor([-1.2], dtype=torch.float64, requires_grad=True)
+    const = torch.tensor([0.1], dtype=torch.float64, requires_grad=True)
+    loss = O.gpcv_neg_elbo(x, y, vm, cv, raw_vol, const)
+    loss.backward()
+    with torch.no_grad():
+        jit = O.GPCV_PRIOR_JITTER
+        vol = torch.sigmoid(raw_vol)
+        K = vol * torch.minimum(x.view(-1, 1), x.view(1, -1)) + jit * torch.eye(n, dtype=torch.float64)
+        Ki = torch.linalg.inv(K)
+        Ls = torch.tril(cv)
+        W = Ki @ Ls
+        d = const - vm
+        alpha = Ki @ d
+        t, w = O.gauss_hermite(75, torch.float64)
+        s = (Ls ** 2).sum(-1)
+        f = (2 * s).sqrt().unsqueeze(-1) * t + vm.unsqueeze(-1)
+        ef = f.exp()
+        dl = torch.where(ef > 1e-3, (y.unsqueeze(-1) / ef.clamp(min=1e-3)) ** 2 - 1.0, torch.zeros_like(f))
+        gm = (w * dl).sum(-1) / math.sqrt(math.pi)
+        gs = (w * dl * t).sum(-1) / math.sqrt(math.pi) / (2 * s).sqrt()
+        g_cv = torch.tril(-2 * gs.unsqueeze(-1) * Ls + W - torch.diag(1.0 / torch.diagonal(Ls))) / n
+        g_vm = (-gm - alpha) / n
+        g_c = alpha.sum() / n
+        q, trKS, WW = d @ alpha, (W * Ls).sum(), (W ** 2).sum()
+        dkl = (n - jit * torch.trace(Ki) - trKS - q + jit * (WW + alpha @ alpha)) / (2 * vol)
+        g_raw = dkl * vol * (1 - vol) / n
+    close(cv.grad, g_cv, rtol=1e-8, atol=1e-10)
+    close(vm.grad, g_vm, rtol=1e-8, atol=1e-10)
+    close(const.grad, g_c.reshape(1), rtol=1e-8, atol=1e-10)
+    close(raw_vol.grad, g_raw, rtol=1e-8, atol=1e-10)
+
+
+def test_gpcv_oracle_learns_volatility_level():
+    """A few hundred Adam steps move the predicted scale from the running-std initialisation towards the true volatility."""
+    x, vol, logy = O.synth_series(1, 49)
+    px = logy[0].exp()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pred, st = O.learn_gpcv(x[:48], px, train_iters=60, eps=torch.zeros(48, 10), return_state=True)
+    assert st["losses"][-1] < st["losses"][0]
+    assert torch.isfinite(pred).all() and pred.shape == (48,)
+    assert 0.02 < float(pred.mean()) < 2.0

@@ -484,4 +484,18 @@ int volt_rollout_stats(const float* samples, int B, int S, int H, const float* t
   return launch_rollout_stats(samples, B, S, H, truth, strike, exp_flag, ecdf, mean, sd, nll, payoff, ST(stream));
 }
 
+int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t,
+                   const float* gh_w, int nq, int B, int n, float inv_n, float* grad_chol, float* rows, void* stream) {
+  VOLT_REQUIRE(chol_var && W && var_mean && y && gh_t && gh_w && grad_chol && rows, "volt_gpcv_rows: null pointer");
+  VOLT_REQUIRE(B >= 1 && n >= 1 && nq >= 1 && nq <= 128, "volt_gpcv_rows: need B, n >= 1 and 1 <= nq <= 128 (got %d, %d, %d)", B, n, nq);
+  return launch_gpcv_rows(chol_var, W, var_mean, y, gh_t, gh_w, nq, B, n, inv_n, grad_chol, rows, ST(stream));
+}
+
+int volt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
+                   float beta2, float eps, int step, void* stream) {
+  VOLT_REQUIRE(param && grad && exp_avg && exp_avg_sq, "volt_adam_step: null pointer");
+  VOLT_REQUIRE(count >= 1 && step >= 1, "volt_adam_step: need count >= 1 and step >= 1");
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, step, ST(stream));
+}
+
 }  // extern "C"

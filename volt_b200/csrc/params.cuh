@@ -57,6 +57,10 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st);   // tcgen05 3xTF32 ten
 int mll_tc_resident_ctas(int T, int two_rhs);              // series in flight per launch of that kernel
 int launch_mll_large(const MllParams& p, int b, cudaStream_t st);  // multi-CTA path for one long series (chol_large.cu)
 int launch_rollout(RolloutParams p, cudaStream_t st);
+int launch_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t, const float* gh_w,
+                     int nq, int B, int n, float inv_n, float* grad_chol, float* rows, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, long long count, float lr, float beta1, float beta2, float eps, int step,
+                cudaStream_t st);
 int launch_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag, float* ecdf,
                          float* mean, float* sd, float* nll, float* payoff, cudaStream_t st);
 int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kind, float theta, const float* latent, float* out,

@@ -1,0 +1,144 @@
+"""GPCV stage on the GPU -- LearnGPCV (voltron/train_utils.py:15-67), the step before the hot path that produces the vol
+path.  B independent series are trained at once, device resident, with analytic gradients:
+
+  * the T^3 pieces per iteration -- factorisation of K = vol min(x,x') + 1e-3 I, logdet K, tr K^-1, K^-1 (c - m) -- come
+    from the batched MLL kernel (`volt_mll_grad_bm`) and the batched potrf (`volt_potrf`);
+  * W = K^-1 L_S is two triangular solves with a T x T right-hand side: a plain library call (torch.cholesky_solve -> cuBLAS trsm);
+  * `volt_gpcv_rows` turns them into the per-point Gauss-Hermite likelihood terms, the loss pieces and the gradient of the
+    T x T variational factor; `volt_adam_step` is the optimiser over the flat parameter buffer.
+
+[GPyTorch slice restated from memory, see oracle.volt_oracle: parity with the reference is unpinned for this stage.]
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import S_INVQUAD, S_LOGDET, S_TRINV
+
+PRIOR_JITTER = 1e-3      # [GPyTorch] UnwhitenedVariationalStrategy.prior_distribution: add_jitter() default
+NUM_GH = 75              # train_utils.py:52
+NUM_LIK_SAMPLES = 10     # [GPyTorch] settings.num_likelihood_samples (Likelihood.marginal)
+
+
+def scaled_returns(train_x, train_y):
+    """train_utils.py:16-18.  train_x (n,), train_y (..., n+1) prices -> (..., n)."""
+    dt = train_x[1] - train_x[0]
+    return (train_y[..., 1:] - train_y[..., :-1]) / train_y[..., :-1] / (dt ** 0.5)
+
+
+def _running_std(y):
+    """stack([y[:i].std(0) for i in range(n)]) along the last axis without the O(n^2) loop (single_task_variational_gp.py:216)."""
+    n = y.shape[-1]
+    yd = y.double()
+    c1 = torch.cumsum(yd, -1)
+    c2 = torch.cumsum(yd * yd, -1)
+    cnt = torch.arange(1, n + 1, dtype=torch.float64, device=y.device)
+    var = (c2 - c1 * c1 / cnt) / (cnt - 1)                     # unbiased variance of y[:i+1]; NaN (0/0) for a single value
+    out = torch.full_like(yd, float("nan"))
+    out[..., 2:] = var[..., 1:-1].clamp_min(0).sqrt()          # entry i uses y[:i]
+    return out.to(y.dtype)
+
+
+def init_variational(x, y, vol0=0.2):
+    """SingleTaskVariationalGP.initialize_variational_parameters, param="exp" (single_task_variational_gp.py:204-253).
+    x (n,), y (B,n) on the GPU -> (variational_mean (B,n), chol_variational_covar (B,n,n))."""
+    B, n = y.shape
+    rs = _running_std(y)
+    rs[..., :10] = rs[..., 10:11]
+    f = rs.clamp(min=1e-4).log()
+    ih = (0.5 * y.pow(-2.0) * (f * 2.0).exp()).clamp(min=1e-4, max=1000.0)          # diagonal of the inverse Hessian
+    kuu = vol0 * torch.minimum(x.view(-1, 1), x.view(1, -1))
+    Lk, _, _ = ops.potrf(kuu, check=False)                     # LazyTensor.cholesky() -> psd_safe_cholesky (x[0] = 0: singular)
+    # inner = Lk^T diag(ih) Lk + I (clamp(min=1e-4) fills the off-diagonal of the diag_embed'ed matrix with 1e-4 as well)
+    H = torch.diag_embed(ih).clamp(min=1e-4, max=1000.0)
+    inner = Lk.t().unsqueeze(0) @ H @ Lk.unsqueeze(0) + torch.eye(n, device=y.device)
+    Li, _, _ = ops.potrf(inner, check=False)
+    S = Lk.unsqueeze(0) @ ops.potrs(Li, Lk.t().unsqueeze(0).expand(B, n, n).contiguous())
+    S_root, _, _ = ops.potrf(S, check=False)                   # root_decomposition(method="cholesky")
+    return f, torch.tril(S_root) * 10.0
+
+
+class _State:
+    pass
+
+
+def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=False, return_state=False):
+    """Batched LearnGPCV.  train_x (n,), train_y (B,n+1) or (n+1,) prices.  Returns pred_scale (B,n) on the GPU
+    (train_utils.py:62-67: `likelihood(model(train_x), return_gaussian=False).scale.mean(0)` over 10 function samples;
+    eps (B,n,10) fixes their base normals)."""
+    dev = ops._dev()
+    lib = _lib.load()
+    x = ops._f32(train_x, dev).reshape(-1)
+    n = x.numel()
+    py = ops._f32(train_y, dev).reshape(-1, n + 1)
+    B = py.shape[0]
+    y = scaled_returns(x, py).contiguous()
+    vm0, cv0 = init_variational(x, y)
+    # flat parameter buffer: [variational_mean | chol_variational_covar | constant | raw_vol]  (model.parameters() order)
+    nm, nc = B * n, B * n * n
+    P = torch.empty(nm + nc + 2 * B, device=dev)
+    P[:nm] = vm0.reshape(-1)
+    P[nm:nm + nc] = cv0.reshape(-1)
+    P[nm + nc:nm + nc + B] = 0.0                                                   # ConstantMean
+    P[nm + nc + B:] = math.log(0.2 / 0.8)                                          # BMKernel(vol=0.2): logit
+    G = torch.zeros_like(P)
+    M1 = torch.zeros_like(P)
+    M2 = torch.zeros_like(P)
+    vm, cv = P[:nm].view(B, n), P[nm:nm + nc].view(B, n, n)
+    const, raw_vol = P[nm + nc:nm + nc + B], P[nm + nc + B:]
+    g_vm, g_cv = G[:nm].view(B, n), G[nm:nm + nc].view(B, n, n)
+    g_const, g_raw = G[nm + nc:nm + nc + B], G[nm + nc + B:]
+    t, w = np.polynomial.hermite.hermgauss(NUM_GH)
+    gh_t = torch.as_tensor(t, dtype=torch.float32, device=dev)
+    gh_w = torch.as_tensor(w, dtype=torch.float32, device=dev)
+    Mmin = torch.minimum(x.view(-1, 1), x.view(1, -1))
+    eye = torch.eye(n, device=dev)
+    jit = torch.full((B,), PRIOR_JITTER, device=dev)
+    rows = torch.empty(B, n, 6, device=dev)
+    Lk = torch.empty(B, n, n, device=dev)
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    ju = torch.empty(B, device=dev)
+    inv_n = 1.0 / n
+    losses = []
+    for it in range(1, train_iters + 1):
+        st = ops._stream()
+        vol = torch.sigmoid(raw_vol)
+        d = const.unsqueeze(-1) - vm
+        out = ops.mll_grad("bm", x, vol, d, jit, check=False)                      # logdet K, d^T K^-1 d, tr K^-1, alpha = K^-1 d
+        sc, alpha = out["scalars"], out["alpha"]
+        K = vol.view(B, 1, 1) * Mmin
+        _lib.check(lib.volt_potrf(K.data_ptr(), n * n, n, jit.data_ptr(), 1, B, n, 1e-6, 3, Lk.data_ptr(), n * n, n, ju.data_ptr(),
+                                  info.data_ptr(), st), "volt_potrf")
+        W = torch.cholesky_solve(torch.tril(cv), Lk).contiguous()                  # K^-1 L_S (library trsm x 2; result is column-major)
+        _lib.check(lib.volt_gpcv_rows(cv.data_ptr(), W.data_ptr(), vm.data_ptr(), y.data_ptr(), gh_t.data_ptr(), gh_w.data_ptr(),
+                                      NUM_GH, B, n, inv_n, g_cv.data_ptr(), rows.data_ptr(), st), "volt_gpcv_rows")
+        rs = rows.sum(1)                                                           # (B,6)
+        sumE, trKS, WW, logdetS = rs[:, 0], rs[:, 2], rs[:, 3], 2.0 * rs[:, 4]
+        q, logdetK, trKinv = sc[:, S_INVQUAD], sc[:, S_LOGDET], sc[:, S_TRINV]
+        g_vm.copy_((-rows[:, :, 1] - alpha) * inv_n)
+        g_const.copy_(alpha.sum(-1) * inv_n)
+        dkl_dvol = (n - PRIOR_JITTER * trKinv - trKS - q + PRIOR_JITTER * (WW + (alpha * alpha).sum(-1))) / (2.0 * vol)
+        g_raw.copy_(dkl_dvol * vol * (1.0 - vol) * inv_n)
+        if printing or return_state:
+            kl = 0.5 * (logdetK - logdetS + trKS + q - n)
+            loss = -(sumE - kl) * inv_n
+            if return_state:
+                losses.append(loss.detach().clone())
+            if printing and (it - 1) % 50 == 0:
+                print("Iter %d/%d - Loss: %.3f" % (it, train_iters, float(loss.mean())))
+        _lib.check(lib.volt_adam_step(P.data_ptr(), G.data_ptr(), M1.data_ptr(), M2.data_ptr(), P.numel(), lr, 0.9, 0.999, 1e-8, it,
+                                      st), "volt_adam_step")
+    if eps is None:
+        eps = torch.randn(B, n, NUM_LIK_SAMPLES, device=dev)
+    else:
+        eps = ops._f32(eps, dev).reshape(B, n, -1)
+    fs = (torch.tril(cv) @ eps).transpose(-1, -2) + vm.unsqueeze(1)                 # (B,10,n): MultivariateNormal.rsample
+    pred_scale = fs.exp().clamp(min=1e-3).mean(1)
+    if return_state:
+        s = _State()
+        s.var_mean, s.chol_var, s.constant, s.raw_vol, s.y = vm.clone(), cv.clone(), const.clone(), raw_vol.clone(), y
+        s.losses = torch.stack(losses, 0) if losses else None
+        return pred_scale, s
+    return pred_scale

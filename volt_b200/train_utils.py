@@ -101,3 +101,18 @@ def TrainVoltMagpieModel(train_x, train_y, vol_model, vol_lh, vol_path, train_it
     _train_mode(voltron, voltron_lh)
     _adam_mll_loop(voltron, voltron_lh, train_x, train_y.log(), 0.1, train_iters, printing)
     return voltron, voltron_lh
+
+
+def LearnGPCV(train_x, train_y, train_iters=1000, printing=False, early_stopping=False, kernel="bm"):
+    """voltron/train_utils.py:15-67 -- fit the GPCV variational GP to the scaled returns of one price series and return
+    the predicted volatility path (n,) on train_x's device.  Runs device resident with analytic gradients
+    (volt_b200.gpcv); many series at once: volt_b200.gpcv.learn_gpcv.  Only the Brownian-motion prior of the hot path is
+    provided (kernel="fbm" is outside it)."""
+    from . import gpcv
+
+    if kernel != "bm":
+        raise NotImplementedError("LearnGPCV: only kernel='bm' is provided (FBMKernel is outside the hot path)")
+    x = torch.as_tensor(train_x)
+    pred = gpcv.learn_gpcv(x.reshape(-1), torch.as_tensor(train_y).reshape(1, -1), train_iters=train_iters, printing=printing)
+    return pred[0].to(x.device)
+

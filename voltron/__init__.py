@@ -5,6 +5,7 @@ from volt_b200 import kernels, means, models, option_utils, rollout_utils, train
 from volt_b200.kernels import BMKernel, VolatilityKernel  # noqa: F401
 from volt_b200.models import BMGP, VoltMagpie, VoltronGP  # noqa: F401
 from volt_b200.rollout_utils import GeneratePrediction, Rollouts  # noqa: F401
+from volt_b200.train_utils import LearnGPCV  # noqa: F401
 import sys as _sys
 
 for _n in ("kernels", "means", "models", "option_utils", "rollout_utils", "train_utils"):
