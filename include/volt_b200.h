@@ -112,6 +112,13 @@ int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const
                      int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
                      void* stream);
 
+/* volt_mll_grad_bm that also returns the inverse factor: linv_t (B,T,T) = (L^-1)^T (upper triangular), L the Cholesky
+ * factor of scale*min(x,x') + noise*I.  The GPCV stage needs K^-1 times a T x T matrix every iteration
+ * ([GPyTorch] kl_mvn_mvn inside VariationalELBO, voltron/train_utils.py:46-56): K^-1 M = linv_t (linv_t^T M), two GEMMs. */
+int volt_mll_grad_bm_inv(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise,
+                         int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                         float* linv_t, void* stream);
+
 /* Same for an explicit dense covariance K (B,T,ld) (lower triangle read) + noise_b I  -- the generic
  * MultivariateNormal.log_prob path used when a caller hands over an evaluated kernel matrix. */
 int volt_mll_grad_dense(const float* K, long long k_bstride, int ld, const float* resid, const float* noise, int noise_stride,

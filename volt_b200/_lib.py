@@ -31,6 +31,7 @@ _SIGS = {
     "volt_mll_grad_vol": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp,
                                   c_void_p]),
     "volt_mll_grad_bm": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, c_void_p]),
+    "volt_mll_grad_bm_inv": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_dense": (c_int, [_fp, c_longlong, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp,
                                     c_void_p]),
     "volt_mll_grad_vol_host": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp]),

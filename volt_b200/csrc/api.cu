@@ -131,7 +131,7 @@ int launch_mll_batched(MllParams p, cudaStream_t st) {
     g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
   }
   // A few very long series: one CTA per series would leave the GPU idle -> multi-CTA right-looking path, series by series.
-  if (g_mll_impl && p.resid && !p.resid2 && !p.L_out && !p.z_out && p.T >= 1536 && p.B <= 16) {
+  if (g_mll_impl && p.resid && !p.resid2 && !p.L_out && !p.U_out && !p.z_out && p.T >= 1536 && p.B <= 16) {
     for (int b = 0; b < p.B; ++b) {
       int s = launch_mll_large(p, b, st);
       if (s) return s;
@@ -252,6 +252,21 @@ int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const
   p.x = x;
   p.scale = scale;
   p.scale_stride = scale_stride;
+  return launch_mll_batched(p, ST(stream));
+}
+
+int volt_mll_grad_bm_inv(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise, int noise_stride,
+                         int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, float* linv_t,
+                         void* stream) {
+  VOLT_REQUIRE(x && scale && resid && scalars && linv_t, "volt_mll_grad_bm_inv: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 1, "volt_mll_grad_bm_inv: need B,T >= 1");
+  VOLT_REQUIRE(g_mll_impl, "volt_mll_grad_bm_inv: needs the tensor-core implementation (VOLT_MLL_IMPL=tc)");
+  MllParams p = base_params(B, T, resid, noise, noise_stride, jitter, max_tries, scalars, alpha, info);
+  p.kind = KIND_BM;
+  p.x = x;
+  p.scale = scale;
+  p.scale_stride = scale_stride;
+  p.U_out = linv_t;
   return launch_mll_batched(p, ST(stream));
 }
 

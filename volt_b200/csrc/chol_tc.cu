@@ -335,6 +335,18 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
       }
       if (p.info) p.info[b] = fail;
     }
+    if (p.U_out && p.do_inverse) {
+      // (L^-1)^T: strictly-upper 64-blocks live in the scratch, the diagonal blocks in dinv (dinv[j][r][c] = Linv_jj[c][r])
+      float* Uo = p.U_out + (size_t)b * T * T;
+      for (int idx = tid; idx < T * T; idx += NT) {
+        const int r = idx / T, cc = idx - r * T;
+        const int rb = r >> 6, cb = cc >> 6;
+        float v = 0.f;
+        if (rb < cb) v = S[(size_t)r * ld + cc];
+        else if (rb == cb) v = dinv[((size_t)rb * NB + (r & 63)) * NB + (cc & 63)];
+        Uo[idx] = v;
+      }
+    }
     if (p.L_out) {
       float* Lo = p.L_out + (size_t)b * p.L_bstride;
       for (int idx = tid; idx < T * T; idx += NT) {

@@ -23,6 +23,7 @@ struct MllParams {
   float* alpha;                         // (B,T) or null
   int* info;                            // (B) or null
   float* L_out; long long L_bstride; int ldl;
+  float* U_out;                         // optional (B,T,T) contiguous: (L^-1)^T, upper triangular (tensor-core kernel, needs do_inverse)
   int do_inverse;
   float jitter; int max_tries;
   float* scratch;                       // gridDim.x * Tp * Tp

@@ -1,9 +1,9 @@
 """GPCV stage on the GPU -- LearnGPCV (voltron/train_utils.py:15-67), the step before the hot path that produces the vol
 path.  B independent series are trained at once, device resident, with analytic gradients:
 
-  * the T^3 pieces per iteration -- factorisation of K = vol min(x,x') + 1e-3 I, logdet K, tr K^-1, K^-1 (c - m) -- come
-    from the batched MLL kernel (`volt_mll_grad_bm`) and the batched potrf (`volt_potrf`);
-  * W = K^-1 L_S is two triangular solves with a T x T right-hand side: a plain library call (torch.cholesky_solve -> cuBLAS trsm);
+  * the T^3 pieces per iteration -- factorisation of K = vol min(x,x') + 1e-3 I, logdet K, tr K^-1, K^-1 (c - m) and the
+    inverse factor (L^-1)^T -- come from ONE launch of the batched tensor-core MLL kernel (`volt_mll_grad_bm_inv`);
+  * W = K^-1 L_S = U (U^T L_S) is two plain library GEMMs (torch.bmm -> cuBLAS, fp32);
   * `volt_gpcv_rows` turns them into the per-point Gauss-Hermite likelihood terms, the loss pieces and the gradient of the
     T x T variational factor; `volt_adam_step` is the optimiser over the flat parameter buffer.
 
@@ -93,25 +93,23 @@ def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=F
     t, w = np.polynomial.hermite.hermgauss(NUM_GH)
     gh_t = torch.as_tensor(t, dtype=torch.float32, device=dev)
     gh_w = torch.as_tensor(w, dtype=torch.float32, device=dev)
-    Mmin = torch.minimum(x.view(-1, 1), x.view(1, -1))
-    eye = torch.eye(n, device=dev)
     jit = torch.full((B,), PRIOR_JITTER, device=dev)
     rows = torch.empty(B, n, 6, device=dev)
-    Lk = torch.empty(B, n, n, device=dev)
+    U = torch.empty(B, n, n, device=dev)
+    sc = torch.empty(B, 16, device=dev)
+    alpha = torch.empty(B, n, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
-    ju = torch.empty(B, device=dev)
     inv_n = 1.0 / n
     losses = []
     for it in range(1, train_iters + 1):
         st = ops._stream()
         vol = torch.sigmoid(raw_vol)
-        d = const.unsqueeze(-1) - vm
-        out = ops.mll_grad("bm", x, vol, d, jit, check=False)                      # logdet K, d^T K^-1 d, tr K^-1, alpha = K^-1 d
-        sc, alpha = out["scalars"], out["alpha"]
-        K = vol.view(B, 1, 1) * Mmin
-        _lib.check(lib.volt_potrf(K.data_ptr(), n * n, n, jit.data_ptr(), 1, B, n, 1e-6, 3, Lk.data_ptr(), n * n, n, ju.data_ptr(),
-                                  info.data_ptr(), st), "volt_potrf")
-        W = torch.cholesky_solve(torch.tril(cv), Lk).contiguous()                  # K^-1 L_S (library trsm x 2; result is column-major)
+        d = (const.unsqueeze(-1) - vm).contiguous()
+        # one fused build + potrf + trtri of K = vol min(x,x') + 1e-3 I per series: logdet K, d^T K^-1 d, tr K^-1,
+        # alpha = K^-1 d and the inverse factor U = (L^-1)^T
+        _lib.check(lib.volt_mll_grad_bm_inv(x.data_ptr(), vol.data_ptr(), 1, d.data_ptr(), jit.data_ptr(), 1, B, n, 1e-6, 3,
+                                            sc.data_ptr(), alpha.data_ptr(), info.data_ptr(), U.data_ptr(), st), "volt_mll_grad_bm_inv")
+        W = torch.bmm(U, torch.bmm(U.transpose(1, 2), torch.tril(cv)))              # K^-1 L_S: two library GEMMs
         _lib.check(lib.volt_gpcv_rows(cv.data_ptr(), W.data_ptr(), vm.data_ptr(), y.data_ptr(), gh_t.data_ptr(), gh_w.data_ptr(),
                                       NUM_GH, B, n, inv_n, g_cv.data_ptr(), rows.data_ptr(), st), "volt_gpcv_rows")
         rs = rows.sum(1)                                                           # (B,6)
