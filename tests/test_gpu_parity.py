@@ -668,3 +668,30 @@ def test_learn_gpcv_mirror_api(vb):
     assert out.shape == (40,) and out.device.type == "cpu" and bool(torch.isfinite(out).all()) and float(out.min()) >= 1e-3
     with pytest.raises(NotImplementedError):
         voltron.train_utils.LearnGPCV(x[:40], logy[0].exp(), train_iters=1, kernel="fbm")
+
+
+def test_full_pipeline_gpcv_to_evaluation(vb):
+    """The reference's per-ticker flow (experiments/stocks/GenerateMultiMeanPreds.py:85-128) end to end on the GPU path:
+    prices -> LearnGPCV -> TrainVolModel -> TrainVoltMagpieModel -> Rollouts -> calibration statistics."""
+    import voltron
+    from voltron.train_utils import LearnGPCV, TrainVolModel, TrainVoltMagpieModel
+
+    torch.manual_seed(0)
+    n, H, S = 96, 10, 64
+    x, vol_true, logy = O.synth_series(1, n + 1 + H)
+    px = logy[0].exp()
+    train_x = x[:n]
+    train_y = px[:n + 1]
+    test_x = torch.arange(H) / 252.0 + train_x[-1] + train_x[1]
+    vol = LearnGPCV(train_x, train_y, train_iters=30)
+    assert vol.shape == (n,) and bool(torch.isfinite(vol).all())
+    vmod, vlh = TrainVolModel(train_x, vol, train_iters=20)
+    volt, lh = TrainVoltMagpieModel(train_x, train_y[1:], vmod, vlh, vol, train_iters=20, k=25, mean_func="ewma")
+    vmod.eval()
+    samples = voltron.rollout_utils.Rollouts(train_x, train_y, test_x, volt, nsample=S)
+    assert samples.shape == (S, H) and bool(torch.isfinite(samples).all())
+    st = vb.batched.rollout_stats(samples, truth=logy[0, n + 1:n + 1 + H])
+    assert bool(((st["ecdf"] >= 0) & (st["ecdf"] <= 1)).all()) and bool(torch.isfinite(st["nll"]).all())
+    # the forecast is centred near the last observed log price and its spread grows with the horizon
+    assert abs(float(st["mean"][0, 0]) - float(logy[0, n])) < 0.2
+    assert float(st["std"][0, -1]) > float(st["std"][0, 0])
