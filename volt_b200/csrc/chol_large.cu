@@ -4,8 +4,8 @@
 // batched kernel (chol_tc_dev.cuh).
 //
 //   W  (Tp x Tp): lower triangle = A, overwritten by L            Ut (Tp x Tp): upper triangle = R^T, overwritten by (L^-1)^T
-//   for j:  diag   L_jj = chol(W_jj), Linv_jj, z_j = Linv_jj r_j                               (1 CTA)
-//           panel  W[i,j] <- W[i,j] Linv_jj^T (i > j),  r_i -= W[i,j] z_j                      ((T-R0)/128 CTAs)
+//   for j:  diag + panel in one launch: every CTA factors W_jj (Linv_jj, z_j = Linv_jj r_j), then
+//                  W[i,j] <- W[i,j] Linv_jj^T (i > j),  r_i -= W[i,j] z_j                      ((T-R0)/128 CTAs)
 //           update W[i,c] -= W[i,j] W[c,j]^T  (j < c <= i)                                      (tiles)
 //   for k:  final  Ut[0:k+1, k] <- Ut[0:k+1, k] Linv_kk^T;  tr += |.|^2, alpha += (.) z_k       ((k+1)/2 CTAs)
 //           update Ut[n, i] -= Ut[n, k] W[i, k]^T  (n <= k < i)                                  (tiles)
@@ -29,7 +29,8 @@ struct LargeParams {
   float scale, dadd;
   const float* resid;  // (T)
   float* W; float* Ut; float* dinv;
-  float* z;            // (Tp): residual, overwritten by z = L^-1 r
+  float* z;            // (Tp): residual, updated right-looking (r_i -= W[i,j] z_j)
+  float* zf;           // (Tp): z = L^-1 r, block j written by CTA 0 of step j
   float* alpha;        // (Tp)
   float* acc;          // [0] sum log L_ii, [1] tr(A^-1)
   float* origd;        // (Tp) original diagonal of A (pivot failure predicate)
@@ -74,8 +75,8 @@ __device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_t
   c.Vs = reinterpret_cast<float*>(base + VEC_OFF);
   c.z = c.Vs; c.al = c.Vs; c.z2 = c.Vs;
   c.diagl = c.Vs;                 // 64
-  c.tmp = c.diagl + NB;           // 128
-  c.red = c.tmp + 2 * NB;         // 32
+  c.tmp = c.diagl + NB;           // 192: [0,64) origd then z_j, [64,192) z residual / per-row half sums
+  c.red = c.tmp + 3 * NB;         // 32
   c.flag = reinterpret_cast<int*>(c.red + 32);
   c.bar = reinterpret_cast<uint64_t*>(c.red + 36);
   uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(c.red + 40);   // c.bar holds two mbarriers (16 bytes)
@@ -104,43 +105,76 @@ __device__ __forceinline__ void cta_teardown(Shared& sh) {
   __syncthreads();
   if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(sh.c.tmem) : "memory");
 }
-constexpr size_t LARGE_SMEM = VEC_OFF + sizeof(float) * (NB + 2 * NB + 32 + 12);
+constexpr size_t LARGE_SMEM = VEC_OFF + sizeof(float) * (NB + 3 * NB + 32 + 12);
 
-// ---- diagonal block of step j (one CTA)
-__global__ void __launch_bounds__(NT, 1) large_diag_kernel(LargeParams p, int j) {
+// ---- step j of the factorisation: diagonal block + panel in ONE launch.  Every CTA factors and inverts the 64 x 64
+// diagonal block itself (10 us of redundant work instead of a 1-CTA kernel and a launch boundary on the critical
+// path: 128 of them at T = 8192), CTA 0 publishes Linv_jj / z_j / log-det / the failure flag, then CTA b solves its
+// 128 panel rows W[i,j] <- W[i,j] Linv_jj^T and updates the residual r_i -= W[i,j] z_j.  L_jj itself is not written
+// back: nothing reads the diagonal blocks of W again.
+__global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, int j) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Shared sh;
-  cta_setup(sh, smem_raw, false);
+  cta_setup(sh, smem_raw, true);
   Ctx& c = sh.c;
-  const int tid = threadIdx.x, R0 = j * NB, ld = p.Tp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
+  const int R0 = j * NB, ld = p.Tp;
   for (int idx = tid; idx < NB * NB; idx += NT) {
     const int r = idx >> 6, cc = idx & 63;
     c.Ct[r * CLD + cc] = p.W[(size_t)(R0 + r) * ld + R0 + cc];
   }
   if (tid == 0) *c.flag = -1;
-  if (tid < NB) c.tmp[tid] = p.origd[R0 + tid];
+  if (tid < NB) { c.tmp[tid] = p.origd[R0 + tid]; c.tmp[NB + tid] = p.z[R0 + tid]; }
   __syncthreads();
   diag64_block_v2<CLD>(c.Ct, sh.LiT, sh.tmpbuf, c.diagl, c.tmp, c.flag, R0);
   __syncthreads();
-  float* dj = p.dinv + (size_t)j * NB * NB;
-  for (int idx = tid; idx < NB * NB; idx += NT) {
-    const int r = idx >> 6, cc = idx & 63;
-    p.W[(size_t)(R0 + r) * ld + R0 + cc] = (cc <= r) ? c.Ct[r * CLD + cc] : 0.f;
-    dj[idx] = sh.LiT[r * CLD + cc];
-  }
-  if (tid < NB) c.tmp[tid] = p.z[R0 + tid];
+  float zj = 0.f;
+  if (tid < NB)
+    for (int k = 0; k <= tid; ++k) zj = fmaf(sh.LiT[k * CLD + tid], c.tmp[NB + k], zj);
   __syncthreads();
-  if (tid < NB) {
-    float zz = 0.f;
-    for (int k = 0; k <= tid; ++k) zz = fmaf(sh.LiT[k * CLD + tid], c.tmp[k], zz);
-    p.z[R0 + tid] = zz;
+  if (tid < NB) c.tmp[tid] = zj;                       // z_j = Linv_jj r_j (origd is dead)
+  stage_linv_from_lit(c, sh.LiT);
+  if (blockIdx.x == 0) {
+    float* dj = p.dinv + (size_t)j * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += NT) dj[idx] = sh.LiT[(idx >> 6) * CLD + (idx & 63)];
+    if (tid < NB) p.zf[R0 + tid] = zj;
+    float lg = (tid < NB && R0 + tid < p.T) ? logf(c.diagl[tid]) : 0.f;
+    lg = block_sum(lg, c.red);
+    if (tid == 0) {
+      p.acc[0] += lg;                                  // one writer per step, launches are stream-ordered
+      if (*c.flag >= 0 && *p.flag < 0) *p.flag = *c.flag;
+    }
   }
-  float lg = (tid < NB && R0 + tid < p.T) ? logf(c.diagl[tid]) : 0.f;
-  lg = block_sum(lg, c.red);
-  if (tid == 0) {
-    p.acc[0] += lg;                                  // single CTA, launches are stream-ordered
-    if (*c.flag >= 0 && *p.flag < 0) *p.flag = *c.flag;
+  __syncthreads();                                     // LiT / tmpbuf (aliasing the stage region) are dead from here on
+  const int r_base = R0 + NB + CM * blockIdx.x, row_end = p.Tp;
+  if (r_base < row_end) {
+    const int gr = r_base + row;
+    float s[32], o[32];
+    if (gr < row_end) {
+      const float4* src = reinterpret_cast<const float4*>(p.W + (size_t)gr * ld + R0 + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[q];
+        s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) s[q] = 0.f;
+    }
+    trsm_tc(c, s, o, row, half_id);
+    {
+      const int g0 = r_base + 32 * (warp & 3);
+      if (g0 < row_end) store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, p.W + (size_t)g0 * ld + R0 + c0, ld, lane);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) dot = fmaf(o[q], c.tmp[c0 + q], dot);
+    if (half_id) c.tmp[NB + row] = dot;                // the two column halves of a row are combined in a fixed order
+    __syncthreads();
+    if (half_id == 0 && gr < row_end) p.z[gr] -= dot + c.tmp[NB + row];
   }
+  cta_teardown(sh);
 }
 
 // ---- panel (mode 0: Cholesky panel of step j; mode 1: finalise block row j of the inverse)
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j
   if (gr < row_end) {
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
-      dot = fmaf(o[q], p.z[R0 + c0 + q], dot);
+      dot = fmaf(o[q], (mode ? p.zf : p.z)[R0 + c0 + q], dot);
       if (mode && gr < p.T && R0 + c0 + q < p.T) sq = fmaf(o[q], o[q], sq);
     }
   }
@@ -238,7 +272,7 @@ __global__ void __launch_bounds__(256) large_finish_kernel(LargeParams p, float 
   __shared__ float red[32];
   float zz = 0.f, aa = 0.f, ar = 0.f;
   for (int i = threadIdx.x; i < p.T; i += 256) {
-    const float zi = p.z[i], ai = p.alpha[i];
+    const float zi = p.zf[i], ai = p.alpha[i];
     zz = fmaf(zi, zi, zz);
     aa = fmaf(ai, ai, aa);
     ar = fmaf(ai, p.resid[i], ar);
@@ -272,7 +306,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   if (s) return s;
   s = get_workspace(tp2 * sizeof(float), &u, 10);
   if (s) return s;
-  const size_t aux_fl = (size_t)p.nb * NB * NB + 3 * (size_t)p.Tp + 16;
+  const size_t aux_fl = (size_t)p.nb * NB * NB + 4 * (size_t)p.Tp + 16;
   s = get_workspace(aux_fl * sizeof(float), &aux, 11);
   if (s) return s;
   p.W = (float*)w;
@@ -281,7 +315,8 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   p.z = p.dinv + (size_t)p.nb * NB * NB;
   p.alpha = p.z + p.Tp;
   p.origd = p.alpha + p.Tp;
-  p.acc = p.origd + p.Tp;
+  p.zf = p.origd + p.Tp;
+  p.acc = p.zf + p.Tp;
   p.flag = reinterpret_cast<int*>(p.acc + 4);
   if (mp.kind == KIND_VOL) p.V = mp.V + (size_t)b * mp.T;
   else if (mp.kind == KIND_BM) { p.V = mp.x; }
@@ -294,7 +329,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   p.scale = scale;
   static bool attr = false;
   if (!attr) {
-    VOLT_CUDA(cudaFuncSetAttribute(large_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
+    VOLT_CUDA(cudaFuncSetAttribute(large_diagpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     VOLT_CUDA(cudaFuncSetAttribute(large_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     VOLT_CUDA(cudaFuncSetAttribute(large_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     attr = true;
@@ -349,10 +384,9 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     bool rest_pending = false;
     for (int j = 0; j < p.nb; ++j) {
       const int R0 = j * NB, panel_end = min(p.Tp, (j / PB + 1) * PB * NB);
-      large_diag_kernel<<<1, NT, LARGE_SMEM, st>>>(p, j);
       const int rows = p.Tp - (R0 + NB);
+      large_diagpanel_kernel<<<max(1, (rows + CM - 1) / CM), NT, LARGE_SMEM, st>>>(p, j);
       if (rows > 0) {
-        large_panel_kernel<<<(rows + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, j, 0);
         update(st, 0, R0 + NB, p.Tp, R0 + NB, panel_end, R0, R0 + NB);                  // inside the panel, K = 64
         if (R0 + NB == panel_end) { s = deferred(0, panel_end, rest_pending); if (s) return s; }
       }
