@@ -313,8 +313,11 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   void* vres = nullptr;
   s = get_workspace(bt * sizeof(float), &vres, 1);   // reserve the prefix-sum buffer at full size (no regrow mid-pipeline)
   if (s) return s;
-  const int slots = mll_tc_resident_ctas(T, 0);
-  const int B0 = (B >= 2 * slots) ? slots : B;
+  // first chunk: VOLT_E2E_CHUNK0 series (developer knob), default two series per SM -- large enough to keep the GPU busy while
+  // the rest is copied, small enough that its own copy (the only exposed one) stays short
+  static const int chunk0_env = [] { const char* e = getenv("VOLT_E2E_CHUNK0"); return e ? atoi(e) : 0; }();
+  const int slots = chunk0_env > 0 ? chunk0_env : 2 * sm_count();
+  const int B0 = (B >= 2 * slots && B >= 2 * mll_tc_resident_ctas(T, 0)) ? slots : B;
   const size_t n0 = (size_t)B0 * T;
   VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_noise, noise, n_noise * 4, cudaMemcpyHostToDevice, s_copy));
