@@ -315,19 +315,22 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
   uint8_t* BH = c.X + Y_BH;
   uint8_t* BL = c.X + Y_BL;
   float4 ra[4], rb[2];
-  auto gload = [&](int k0) {
+  auto gload_b = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
       rb[i] = *reinterpret_cast<const float4*>(S + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
     }
+  };
+  auto gload_a = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
       ra[i] = load_a<PHASE_B>(S, ld, a_row0 + r, a_row_end, k0 + chunk * 4, dinv);
     }
   };
-  gload(k_lo);
+  gload_b(k_lo);
+  gload_a(k_lo);
   for (int kt = 0; kt < nk; ++kt) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {   // the raw tile is not an MMA operand: refill it while the previous MMAs still run
@@ -340,7 +343,10 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
       const int idx = tid + NT * i;
       st_split(BH, BL, idx >> 3, idx & 7, rb[i]);
     }
-    if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
+    if (kt + 1 < nk) {
+      gload_b(k_lo + (kt + 1) * 32);
+      gload_a(k_lo + (kt + 1) * 32);
+    }
     __syncthreads();
     {
       uint32_t hi[16], lo[16];
