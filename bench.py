@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=32, help="series timed on the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true", help="skip the secondary rollout-throughput measurement")
     args = ap.parse_args()
 
     import torch
@@ -245,10 +246,36 @@ def main():
     clocks = sampler.finish()
     assert abs(float(hs[:, 0].sum()) + loss) < 1e-2 * abs(loss) + 1e-3 or world > 1
 
-    t = torch.tensor([total_ms, e2e_t * 1e3, kern_ms], device=dev, dtype=torch.float64)
+    # secondary metric of BASELINE.json's north_star: Monte-Carlo rollout throughput on the c4 per-GPU share
+    # (512 series x 512 draws x 30 steps, T=256, EWMA k=25, Philox normals in-kernel); reported, not the headline
+    roll = None
+    if args.workload == "c2" and not args.no_rollout:
+        rB, rT, rS, rH = 512, 256, 512, 30
+        rx, rvol, rlogy = batched.synth_series(rB, rT, dt, start=rank * rB)
+        g = torch.Generator().manual_seed(1 + rank)
+        rpv = (rvol[:, -1:, None] * torch.exp(0.1 * torch.randn(rB, rS, rH, generator=g))).to(dev)
+        rxd, rvd, ryd = rx.to(dev), rvol.to(dev), rlogy.to(dev)
+        for _ in range(3):
+            ops.rollout(rxd, ryd, rvd, rpv, eps=None, k=K_EWMA, seed=3, check=False)
+        torch.cuda.synchronize()
+        rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in rev:
+            a.record()
+            ops.rollout(rxd, ryd, rvd, rpv, eps=None, k=K_EWMA, seed=3, check=False)
+            b.record()
+        torch.cuda.synchronize()
+        roll_ms = sum(a.elapsed_time(b) for a, b in rev) / len(rev)
+    else:
+        roll_ms = 0.0
+
+    t = torch.tensor([total_ms, e2e_t * 1e3, kern_ms, roll_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms = (float(v) for v in t)
+    total_ms, e2e_ms, kern_ms, roll_ms = (float(v) for v in t)
+    if roll_ms > 0:
+        roll = dict(metric="rollout step-samples/sec", value=512 * 512 * 30 * world / (roll_ms * 1e-3), unit="step-samples/s",
+                    ms_per_call=roll_ms, config="c4 per-GPU share: 512 series x 512 draws x 30 steps, T=256, ewma k=25, Philox in-kernel",
+                    path_samples_per_s=512 * 512 * world / (roll_ms * 1e-3))
     value = B * world * args.steps / (total_ms * 1e-3)
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
 
@@ -276,6 +303,7 @@ def main():
                  d2h_bytes_per_step=int(B * 16 * 4 + B * 4)),
         gpu_launches=int(launches),
         clocks=clocks,
+        rollout=roll,
         roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=traffic,
                       kernel="mll_batched_tc_kernel (+ cumtrapz_kernel, <1% of the time)", ms_per_launch=kern_ms, bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
         roofline_tensor=dict(bound="tensor", achieved=ach_tf, peak=pk["tf"], unit="TFLOP/s", frac=ach_tf / pk["tf"],
