@@ -96,7 +96,8 @@ def test_ma_means_vs_oracle(vb, kind, T, k):
 
 
 # ------------------------------------------------------------------------------------------------ exact MLL + grad
-@pytest.mark.parametrize("T", [2, 17, 48, 64, 65, 100, 128, 200, 256, 399, 512])
+# 700 / 832: the longest series of the three-CTA-per-SM kernel instance; 900: the first size of the two-CTA instance
+@pytest.mark.parametrize("T", [2, 17, 48, 64, 65, 100, 128, 200, 256, 399, 512, 700, 832, 900])
 def test_mll_grad_vol_vs_oracle(vb, T):
     B, k = 3, 10
     x, vol, logy = O.synth_series(B, T)

@@ -406,7 +406,7 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.nb = p.Tp / NB;
   const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12);
   const size_t smem_total = 233472, smem_cta_reserved = 1024;   // sm_100: 228 KB per SM, 1 KB reserved per resident CTA
-  // three resident CTAs per SM when the small shared-memory map fits three times (T <= ~640); VOLT_TC_CTAS=2 forces the
+  // three resident CTAs per SM when the small shared-memory map fits three times (T <= 832); VOLT_TC_CTAS=2 forces the
   // double-buffered two-CTA kernel (A/B timing)
   static const int force2 = [] { const char* e = getenv("VOLT_TC_CTAS"); return (e && e[0] == '2') ? 1 : 0; }();
   const size_t smem3 = tc::Y_VEC_OFF + vec;

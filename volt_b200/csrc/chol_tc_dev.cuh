@@ -290,7 +290,7 @@ static __device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// "Three CTAs per SM" building blocks (series with T <= 640).  The kernel is latency bound (ncu: issue slots 36 %, L1
+// "Three CTAs per SM" building blocks (series short enough for the small shared-memory map: T <= 832).  The kernel is latency bound (ncu: issue slots 36 %, L1
 // data pipe ~35 %, tensor pipe 20 % with two resident CTAs), so the lever is more resident CTAs: 128 TMEM columns and
 // ~71 KB of shared memory per CTA instead of 256 / 106 KB.  The price is single-buffered GEMM stages (the MMAs of a
 // k-tile are waited for before the next tile is staged -- the other two CTAs fill the gap) and a two-pass TRSM.
