@@ -190,9 +190,11 @@ int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean,
                    const float* gh_w, int nq, int B, int n, float inv_n, float* grad_chol, float* rows, void* stream);
 
 /* One torch.optim.Adam step (no weight decay / amsgrad) over a flat parameter buffer: the optimiser of every training
- * loop of the reference (train_utils.py:38-41 lr 0.01; :76-78, :123-125, :236-238 lr 0.01).  step counts from 1. */
+ * loop of the reference (train_utils.py:38-41 lr 0.01; :76-78, :123-125, :236-238 lr 0.01).  step counts from 1; when
+ * step_dev is not NULL the count is read from that device float instead (the caller increments it before each launch),
+ * so that the launch can be replayed from a CUDA graph. */
 int volt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
-                   float beta2, float eps, int step, void* stream);
+                   float beta2, float eps, int step, const float* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -634,7 +634,11 @@ def test_gpcv_rows_and_adam_kernels(vb):
         pt.grad = gr.clone()
         opt.step()
         grd = gr.cuda()
-        assert lib.volt_adam_step(pd.data_ptr(), grd.data_ptr(), m1.data_ptr(), m2.data_ptr(), 1000, 0.01, 0.9, 0.999, 1e-8, step, None) == 0
+        if step % 2:      # host step count and device step counter must agree
+            assert lib.volt_adam_step(pd.data_ptr(), grd.data_ptr(), m1.data_ptr(), m2.data_ptr(), 1000, 0.01, 0.9, 0.999, 1e-8, step, None, None) == 0
+        else:
+            tdev = torch.full((1,), float(step), device="cuda")
+            assert lib.volt_adam_step(pd.data_ptr(), grd.data_ptr(), m1.data_ptr(), m2.data_ptr(), 1000, 0.01, 0.9, 0.999, 1e-8, 0, tdev.data_ptr(), None) == 0
     torch.testing.assert_close(pd.cpu(), pt.detach(), rtol=1e-5, atol=1e-6)
 
 

@@ -510,10 +510,10 @@ int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean,
 }
 
 int volt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
-                   float beta2, float eps, int step, void* stream) {
+                   float beta2, float eps, int step, const float* step_dev, void* stream) {
   VOLT_REQUIRE(param && grad && exp_avg && exp_avg_sq, "volt_adam_step: null pointer");
-  VOLT_REQUIRE(count >= 1 && step >= 1, "volt_adam_step: need count >= 1 and step >= 1");
-  return launch_adam(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, step, ST(stream));
+  VOLT_REQUIRE(count >= 1 && (step >= 1 || step_dev), "volt_adam_step: need count >= 1 and step >= 1 (or a device step counter)");
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, step < 1 ? 1 : step, step_dev, ST(stream));
 }
 
 }  // extern "C"

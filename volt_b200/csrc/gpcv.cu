@@ -82,9 +82,17 @@ __global__ void __launch_bounds__(128) gpcv_rows_kernel(const float* __restrict_
   }
 }
 
-// torch.optim.Adam (no weight decay, no amsgrad): p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// torch.optim.Adam (no weight decay, no amsgrad): p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+// The step count t comes from the host (step_size / inv_sqrt_bc2 precomputed) or, for CUDA-graph replay, from a device
+// float the caller increments before every launch (step_dev != NULL).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long count, float step_size, float beta1, float beta2, float inv_sqrt_bc2, float eps) {
+                            long long count, float step_size, float beta1, float beta2, float inv_sqrt_bc2, float eps, float lr,
+                            const float* __restrict__ step_dev) {
+  if (step_dev) {
+    const float t = *step_dev;
+    step_size = lr / (1.f - powf(beta1, t));
+    inv_sqrt_bc2 = rsqrtf(1.f - powf(beta2, t));
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i];
     const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
@@ -107,12 +115,13 @@ int launch_gpcv_rows(const float* chol_var, const float* W, const float* var_mea
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long count, float lr, float beta1, float beta2, float eps, int step,
-                cudaStream_t st) {
+                const float* step_dev, cudaStream_t st) {
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   long long blocks = (count + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  adam_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, count, (float)(lr / bc1), beta1, beta2, (float)(1.0 / sqrt(bc2)), eps);
+  adam_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, count, step_dev ? 0.f : (float)(lr / bc1), beta1, beta2,
+                                           step_dev ? 0.f : (float)(1.0 / sqrt(bc2)), eps, lr, step_dev);
   return check_cuda(cudaGetLastError(), "adam_kernel");
 }
 

@@ -61,7 +61,7 @@ int launch_rollout(RolloutParams p, cudaStream_t st);
 int launch_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t, const float* gh_w,
                      int nq, int B, int n, float inv_n, float* grad_chol, float* rows, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long count, float lr, float beta1, float beta2, float eps, int step,
-                cudaStream_t st);
+                const float* step_dev, cudaStream_t st);
 int launch_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag, float* ecdf,
                          float* mean, float* sd, float* nll, float* payoff, cudaStream_t st);
 int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kind, float theta, const float* latent, float* out,

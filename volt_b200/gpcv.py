@@ -64,10 +64,10 @@ class _State:
     pass
 
 
-def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=False, return_state=False):
+def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=False, return_state=False, use_graph=True):
     """Batched LearnGPCV.  train_x (n,), train_y (B,n+1) or (n+1,) prices.  Returns pred_scale (B,n) on the GPU
     (train_utils.py:62-67: `likelihood(model(train_x), return_gaussian=False).scale.mean(0)` over 10 function samples;
-    eps (B,n,10) fixes their base normals)."""
+    eps (B,n,10) fixes their base normals).  One Adam iteration (12 launches) is captured in a CUDA graph and replayed."""
     dev = ops._dev()
     lib = _lib.load()
     x = ops._f32(train_x, dev).reshape(-1)
@@ -101,8 +101,13 @@ def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=F
     info = torch.empty(B, dtype=torch.int32, device=dev)
     inv_n = 1.0 / n
     losses = []
-    for it in range(1, train_iters + 1):
+    t_dev = torch.zeros(1, device=dev)                                             # Adam step counter (device: graph replay)
+    loss_dev = torch.zeros(B, device=dev)
+    want_loss = printing or return_state
+
+    def iteration():
         st = ops._stream()
+        t_dev.add_(1.0)
         vol = torch.sigmoid(raw_vol)
         d = (const.unsqueeze(-1) - vm).contiguous()
         # one fused build + potrf + trtri of K = vol min(x,x') + 1e-3 I per series: logdet K, d^T K^-1 d, tr K^-1,
@@ -119,15 +124,41 @@ def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=F
         g_const.copy_(alpha.sum(-1) * inv_n)
         dkl_dvol = (n - PRIOR_JITTER * trKinv - trKS - q + PRIOR_JITTER * (WW + (alpha * alpha).sum(-1))) / (2.0 * vol)
         g_raw.copy_(dkl_dvol * vol * (1.0 - vol) * inv_n)
-        if printing or return_state:
+        if want_loss:
             kl = 0.5 * (logdetK - logdetS + trKS + q - n)
-            loss = -(sumE - kl) * inv_n
-            if return_state:
-                losses.append(loss.detach().clone())
-            if printing and (it - 1) % 50 == 0:
-                print("Iter %d/%d - Loss: %.3f" % (it, train_iters, float(loss.mean())))
-        _lib.check(lib.volt_adam_step(P.data_ptr(), G.data_ptr(), M1.data_ptr(), M2.data_ptr(), P.numel(), lr, 0.9, 0.999, 1e-8, it,
-                                      st), "volt_adam_step")
+            loss_dev.copy_(-(sumE - kl) * inv_n)
+        _lib.check(lib.volt_adam_step(P.data_ptr(), G.data_ptr(), M1.data_ptr(), M2.data_ptr(), P.numel(), lr, 0.9, 0.999, 1e-8, 0,
+                                      t_dev.data_ptr(), st), "volt_adam_step")
+
+    def after(it):
+        if return_state:
+            losses.append(loss_dev.clone())
+        if printing and (it - 1) % 50 == 0:
+            print("Iter %d/%d - Loss: %.3f" % (it, train_iters, float(loss_dev.mean())))
+
+    # warm up eagerly (workspace / cuBLAS handles are not capturable), capture one iteration in a CUDA graph, replay it
+    done = 0
+    for _ in range(min(2, train_iters)):
+        iteration()
+        done += 1
+        after(done)
+    graph = None
+    if done < train_iters and use_graph:
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                iteration()
+            graph = g
+        except Exception:  # noqa: BLE001  (capture unsupported: stay eager on the GPU)
+            graph = None
+    while done < train_iters:
+        if graph is not None:
+            graph.replay()
+        else:
+            iteration()
+        done += 1
+        after(done)
     if eps is None:
         eps = torch.randn(B, n, NUM_LIK_SAMPLES, device=dev)
     else:
