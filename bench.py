@@ -168,7 +168,18 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the first communicator is created; stdout must carry exactly one JSON
+        # line, so file descriptor 1 points at stderr while the process group comes up (init + one collective)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local_rank)))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.require_device()
     dev = torch.device("cuda", local_rank)
 
