@@ -112,7 +112,7 @@ constexpr size_t LARGE_SMEM = VEC_OFF + sizeof(float) * (NB + 3 * NB + 32 + 12);
 // path: 128 of them at T = 8192), CTA 0 publishes Linv_jj / z_j / log-det / the failure flag, then CTA b solves its
 // 128 panel rows W[i,j] <- W[i,j] Linv_jj^T and updates the residual r_i -= W[i,j] z_j.  L_jj itself is not written
 // back: nothing reads the diagonal blocks of W again.
-__global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, int j) {
+__global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, int j, int kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Shared sh;
   cta_setup(sh, smem_raw, true);
@@ -120,9 +120,28 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
   const int R0 = j * NB, ld = p.Tp;
-  for (int idx = tid; idx < NB * NB; idx += NT) {
-    const int r = idx >> 6, cc = idx & 63;
-    c.Ct[r * CLD + cc] = p.W[(size_t)(R0 + r) * ld + R0 + cc];
+  const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
+  // Inside a 256-column panel the updates are LEFT-looking: block column j receives the contributions of the panel's
+  // earlier block columns [kp, R0) right here (K <= 192), so no separate update launch sits between two steps.
+  {
+    float u[32];
+    const bool have = gemm_tc<false>(c, p.W, ld, R0, p.Tp, R0, kp, R0, nullptr);   // rows R0.. (the diagonal block is rows < 64)
+    if (have) {
+      tmem_ld32(c.tmem + t_lane + (uint32_t)c0, u);
+      tc_fence_before();
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) u[q] = 0.f;
+    }
+    if (row < NB) {
+      const float4* src = reinterpret_cast<const float4*>(p.W + (size_t)(R0 + row) * ld + R0 + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[q];
+        *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) =
+            make_float4(v.x - u[4 * q], v.y - u[4 * q + 1], v.z - u[4 * q + 2], v.w - u[4 * q + 3]);
+      }
+    }
   }
   if (tid == 0) *c.flag = -1;
   if (tid < NB) { c.tmp[tid] = p.origd[R0 + tid]; c.tmp[NB + tid] = p.z[R0 + tid]; }
@@ -151,12 +170,20 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
   if (r_base < row_end) {
     const int gr = r_base + row;
     float s[32], o[32];
+    const bool have = gemm_tc<false>(c, p.W, ld, r_base, row_end, R0, kp, R0, nullptr);
+    if (have) {
+      tmem_ld32(c.tmem + t_lane + (uint32_t)c0, s);
+      tc_fence_before();
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) s[q] = 0.f;
+    }
     if (gr < row_end) {
       const float4* src = reinterpret_cast<const float4*>(p.W + (size_t)gr * ld + R0 + c0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 v = src[q];
-        s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+        s[4 * q] = v.x - s[4 * q]; s[4 * q + 1] = v.y - s[4 * q + 1]; s[4 * q + 2] = v.z - s[4 * q + 2]; s[4 * q + 3] = v.w - s[4 * q + 3];
       }
     } else {
 #pragma unroll
@@ -178,7 +205,7 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
 }
 
 // ---- panel (mode 0: Cholesky panel of step j; mode 1: finalise block row j of the inverse)
-__global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j, int mode) {
+__global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j, int mode, int kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Shared sh;
   cta_setup(sh, smem_raw, true);
@@ -192,12 +219,21 @@ __global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j
   const int gr = r_base + row;
   stage_linv_from_dinv(c, p.dinv + (size_t)j * NB * NB);
   float s[32], o[32];
+  // left-looking inside the panel: contributions of the panel's earlier block columns [kp, R0) (B operand rows from W)
+  const bool have = gemm_tc<false>(c, M, ld, r_base, row_end, R0, kp, R0, nullptr, p.W);
+  if (have) {
+    tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, s);
+    tc_fence_before();
+  } else {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s[q] = 0.f;
+  }
   if (gr < row_end) {
     const float4* src = reinterpret_cast<const float4*>(M + (size_t)gr * ld + R0 + c0);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 v = src[q];
-      s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+      s[4 * q] = v.x - s[4 * q]; s[4 * q + 1] = v.y - s[4 * q + 1]; s[4 * q + 2] = v.z - s[4 * q + 2]; s[4 * q + 3] = v.w - s[4 * q + 3];
     }
   } else {
 #pragma unroll
@@ -385,11 +421,8 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     for (int j = 0; j < p.nb; ++j) {
       const int R0 = j * NB, panel_end = min(p.Tp, (j / PB + 1) * PB * NB);
       const int rows = p.Tp - (R0 + NB);
-      large_diagpanel_kernel<<<max(1, (rows + CM - 1) / CM), NT, LARGE_SMEM, st>>>(p, j);
-      if (rows > 0) {
-        update(st, 0, R0 + NB, p.Tp, R0 + NB, panel_end, R0, R0 + NB);                  // inside the panel, K = 64
-        if (R0 + NB == panel_end) { s = deferred(0, panel_end, rest_pending); if (s) return s; }
-      }
+      large_diagpanel_kernel<<<max(1, (rows + CM - 1) / CM), NT, LARGE_SMEM, st>>>(p, j, (j / PB) * PB * NB);
+      if (rows > 0 && R0 + NB == panel_end) { s = deferred(0, panel_end, rest_pending); if (s) return s; }
     }
     s = join(rest_pending);
     if (s) return s;
@@ -403,8 +436,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     bool rest_pending = false;
     for (int k = 0; k < p.nb; ++k) {
       const int R0 = k * NB, rows_done = R0 + NB, panel_end = min(p.Tp, (k / PB + 1) * PB * NB);
-      large_panel_kernel<<<(rows_done + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, k, 1);
-      update(st, 1, 0, rows_done, rows_done, panel_end, R0, rows_done);                 // columns inside the panel, K = 64
+      large_panel_kernel<<<(rows_done + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, k, 1, (k / PB) * PB * NB);
       if (rows_done == panel_end && panel_end < p.Tp) { s = deferred(1, panel_end, rest_pending); if (s) return s; }
     }
     s = join(rest_pending);
