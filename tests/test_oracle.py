@@ -298,3 +298,56 @@ def test_gpcv_oracle_learns_volatility_level():
     assert st["losses"][-1] < st["losses"][0]
     assert torch.isfinite(pred).all() and pred.shape == (48,)
     assert 0.02 < float(pred.mean()) < 2.0
+
+
+# ------------------------------------------------------------------ property tests
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(T=st.integers(2, 40), seed=st.integers(0, 10_000), dt=st.sampled_from([1 / 252, 1 / 365, 0.1]))
+def test_property_vol_kernel_symmetric_psd_and_structured(T, seed, dt):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.arange(T, dtype=torch.float64) * dt
+    vol = torch.exp(0.3 * torch.randn(T, generator=g, dtype=torch.float64)) * 0.2
+    K = O.vol_kernel(x, vol)
+    assert torch.equal(K, K.t())
+    V = O.cum_trapz(vol * vol, x)
+    assert torch.equal(K, V[torch.minimum(torch.arange(T).view(-1, 1), torch.arange(T).view(1, -1))])
+    assert float(torch.linalg.eigvalsh(K).min()) > -1e-12 * float(K.abs().max())
+    # batch == loop and invariance to replication along a batch axis
+    Kb = O.vol_kernel(x, vol.unsqueeze(0).repeat(3, 1))
+    assert all(torch.equal(Kb[i], K) for i in range(3))
+
+
+@settings(max_examples=25, deadline=None)
+@given(T=st.integers(3, 60), k=st.integers(1, 30), seed=st.integers(0, 10_000), shift=st.floats(-5, 5))
+def test_property_ewma_is_a_normalised_causal_filter(T, k, seed, shift):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(T, generator=g, dtype=torch.float64)
+    e = O.ewma(y, k)
+    assert e.shape == (T + 1,)
+    # the filter runs in float32 like the reference's conv1d (EWMA.py:20-37): float32-level tolerances
+    close(O.ewma(y + shift, k).double(), e.double() + shift, rtol=1e-5, atol=1e-5)   # weights sum to one
+    close(O.ewma(3.0 * y, k).double(), 3.0 * e.double(), rtol=1e-5, atol=1e-6)       # linear
+    y2 = y.clone()
+    y2[-1] += 1.0                                                           # causal: e[j] only sees y[:j]
+    assert torch.equal(O.ewma(y2, k)[:T], e[:T])
+    assert float(e[0]) == pytest.approx(float(y[0]), rel=1e-5, abs=1e-6)     # left padding with y[0]
+
+
+@settings(max_examples=20, deadline=None)
+@given(S=st.integers(2, 40), H=st.integers(1, 9), seed=st.integers(0, 10_000))
+def test_property_rollout_stats(S, H, seed):
+    g = torch.Generator().manual_seed(seed)
+    smp = torch.randn(2, S, H, generator=g, dtype=torch.float64)
+    truth = torch.randn(2, H, generator=g, dtype=torch.float64)
+    a = O.rollout_stats(smp, truth=truth, strike=truth)
+    b = O.rollout_stats(smp[:, torch.randperm(S, generator=g)], truth=truth, strike=truth)   # draws are exchangeable
+    for key in a:
+        close(a[key], b[key], rtol=1e-10, atol=1e-12)
+    lo = O.rollout_stats(smp, truth=truth - 1.0)["ecdf"]
+    assert bool((lo <= a["ecdf"]).all()) and bool((a["payoff"] >= 0).all())
+    rep = O.rollout_stats(smp.repeat(1, 3, 1), truth=truth)                # ECDF and mean are invariant to S-fold replication
+    close(rep["ecdf"], a["ecdf"], rtol=0, atol=1e-12)
+    close(rep["mean"], a["mean"], rtol=1e-12, atol=1e-12)
