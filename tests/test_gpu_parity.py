@@ -700,3 +700,29 @@ def test_full_pipeline_gpcv_to_evaluation(vb):
     # the forecast is centred near the last observed log price and its spread grows with the horizon
     assert abs(float(st["mean"][0, 0]) - float(logy[0, n])) < 0.2
     assert float(st["std"][0, -1]) > float(st["std"][0, 0])
+
+
+# ------------------------------------------------------------------------------------------------ ragged / random shapes
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=20, deadline=None)
+@given(B=st.integers(1, 5), T=st.integers(2, 150), seed=st.integers(0, 1000), raw=st.floats(-6.0, 2.0))
+def test_property_random_shapes_cov_and_mll(B, T, seed, raw):
+    """Random (B, T) shapes (T not a multiple of the 64-column block, single rows, ...): covariance bit-exact against the
+    oracle's gather, MLL / gradient within the north_star tolerances against the float64 oracle."""
+    import volt_b200 as vb
+
+    x, vol, logy = O.synth_series(B, T, seed=seed)
+    K = vb.ops.vol_cov(x.cuda(), vol.cuda())
+    for b in range(B):
+        assert torch.equal(K[b].cpu(), O.vol_kernel(x, vol[b]))
+    k = min(10, T)
+    resid = torch.stack([logy[b] - O.ma_mean_forward("ewma", x, logy[b], k, x) for b in range(B)])
+    rawt = torch.full((B,), float(raw))
+    out = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid.cuda(), rawt.cuda(), check=True)
+    for b in range(B):
+        ref = O.volt_mll_and_grad(x.double(), vol[b].double(), resid[b].double(), rawt[b].double())
+        assert relerr(out["mll"][b], ref["mll"]) < 1e-4
+        assert relerr(out["draw_noise"][b], ref["draw_noise"]) < 2e-3
+        assert relerr(out["alpha"][b], ref["alpha"]) < 2e-3
