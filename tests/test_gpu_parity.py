@@ -525,6 +525,49 @@ def test_rollout_singular_training_block_takes_jitter(vb):
     assert relerr(out[0], want) < 1e-3
 
 
+def test_rollout_per_draw_jitter_fallback(vb):
+    """A zero predicted volatility duplicates a row of ONE draw's conditioning matrix from the next step on.  The reference
+    jitters the whole diagonal of that batch member only (psd_safe_cholesky on the (S, m, m) batch, rollout_utils.py:35);
+    the GPU path flags the draw, re-runs it step by step as its own series (ops._redo_flagged_draws) and leaves the other
+    draws untouched.  Oracle: forced down the jitter branch for exactly that member (cf. the singular-block test)."""
+    n, S, H, k = 40, 5, 4, 10
+    x, vol, logy = O.synth_series(1, n, seed=31)
+    g = torch.Generator().manual_seed(9)
+    pred_vol = 0.2 * torch.exp(0.1 * torch.randn(1, S, H, generator=g))
+    s0 = 2
+    pred_vol[0, s0, 1] = 0.0
+    eps = torch.randn(1, S, H, generator=g)
+    base, dbase, _ = vb.ops.rollout(x, logy, vol, pred_vol.clamp_min(1e-3), eps=eps, mean_kind="ewma", k=k, check=False)
+    out, dinfo, sinfo = vb.ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind="ewma", k=k, check=True)
+    assert int(sinfo[0]) == 0 and int(dinfo[0, s0]) & 8 and not int(dinfo[0, s0]) & 5
+    others = [s for s in range(S) if s != s0]
+    assert int(dinfo[0, others].sum()) == 0
+    assert torch.equal(out[0, others], base[0, others])                 # untouched draws are bit-identical
+    px = torch.cat((logy[:, :1], logy), -1).exp()
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    orig = O.psd_safe_cholesky
+
+    def forced(A, jitter=None, **kw):
+        if A.ndim == 3 and A.shape[-1] >= n + 2:      # from the step at which draw s0's matrix holds the duplicated row
+            A = A.clone()
+            A[s0] = A[s0] + 1e-4 * torch.eye(A.shape[-1], dtype=A.dtype)
+            return torch.linalg.cholesky(A)
+        if A.ndim == 3 and A.shape[-1] == 1 and float(A[s0].abs()) < 1e-10:
+            # the zero-volatility test point itself: its 1 x 1 predictive variance is 0 up to rounding of either sign, so
+            # "jitter or not" is a coin flip in any precision; the GPU run saw a tiny positive value (no jitter): mirror it
+            return A.clamp_min(0.0).sqrt()
+        return orig(A, jitter=jitter, **kw)
+
+    O.psd_safe_cholesky = forced
+    try:
+        pv = pred_vol[0].clone().double()
+        pv[s0, 1] = 1e-30                              # log(0) = -inf in the oracle's log-vol bookkeeping; exp(log(1e-30))^2 == 0
+        want = O.rollouts(x.double(), px[0].double(), vol[0].log().double(), test_x.double(), pv, eps[0].double(), k)
+    finally:
+        O.psd_safe_cholesky = orig
+    assert relerr(out[0], want) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ evaluation reductions
 def test_ecdf_and_pricer_goldens(vb, eval_golden):
     """voltron.option_utils.ECDF and the two Pricer reductions against values produced by the reference's own file."""

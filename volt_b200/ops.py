@@ -316,7 +316,9 @@ def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0
     """GeneratePrediction / Rollouts on the GPU -- voltron/rollout_utils.py:6-93.
 
     x (n,), logy (B,n) or (n,), vol (B,n) or (n,), pred_vol (B,S,H) or (S,H), eps like pred_vol or None (Philox).
-    Returns samples (B,S,H) (CUDA), draw_info (B,S), series_info (B)."""
+    Returns samples (B,S,H) (CUDA), draw_info (B,S), series_info (B).  draw_info bits: 1 non-positive pivot in a draw's
+    appended rows, 2 pred_cov needed jitter, 4 not PSD after the retries, 8 the draw was repaired by the per-draw
+    psd_safe_cholesky fallback (its whole matrix re-factored with jitter, step by step; needs explicit eps)."""
     dev = _dev()
     xd = _f32(x, dev).reshape(-1)
     n = xd.numel()
@@ -352,12 +354,53 @@ def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0
                                         float(mr_theta), _ptr(mrl), _ptr(rg), _ptr(mt), use_theta,
                                         float(theta if theta is not None else 0.0), _ptr(lat), int(joint), float(jitter),
                                         int(seed), _ptr(out), _ptr(dinfo), _ptr(sinfo), _stream()), "volt_rollout")
+    if ep is not None and not joint and H > 1 and bool((dinfo & 1).any()):
+        _redo_flagged_draws(out, dinfo, xd, ly, vd, vol_mode, pv, ep, kid, mean_kind, int(k), mr_theta, mrl, rg, mt, theta, lat, jitter)
     if check:
         if bool(sinfo.any()):
             raise NotPSDError("rollout: training covariance not positive definite after jitter retries")
         if bool((dinfo & 5).any()):
             raise NotPSDError("rollout: a conditional covariance was not positive definite after jitter retries")
     return out, dinfo, sinfo
+
+
+def _redo_flagged_draws(out, dinfo, xd, ly, vd, vol_mode, pv, ep, kid, mean_kind, k, mr_theta, mrl, rg, mt, theta, lat, jitter):
+    """Per-draw psd_safe_cholesky fallback (voltron/rollout_utils.py:35 on a batch of per-draw matrices: jitter is added to
+    the WHOLE diagonal of the failing members only).  The rollout kernel shares the n x n factor between the draws of a
+    series, so a draw whose appended rows hit a non-positive pivot (draw_info bit 1) cannot be repaired in place; those
+    draws are re-run the reference's way -- step by step, each as its own series whose conditioning set grows by one
+    point per step, so that the batched potrf kernel's per-matrix jitter retry sees the draw's whole matrix.
+    O(H (n+H)^3) per flagged draw; draws are flagged only on degenerate inputs (zero predicted volatility).
+    Repaired draws get bit 1 cleared and bit 8 set; a draw that still fails keeps bit 1 and gets bit 4."""
+    dev = out.device
+    n, H = xd.numel(), pv.shape[-1]
+    fb, fs = torch.nonzero(dinfo & 1, as_tuple=True)
+    dx = xd[1] - xd[0]
+    sig = vd[fb].exp() if vol_mode == VOL_LOGSIGMA else vd[fb].clone()
+    yh = ly[fb].clone()
+    rh = None if rg is None else rg[fb].clone()
+    res = torch.empty(fb.numel(), H, device=dev)
+    bad = torch.zeros(fb.numel(), dtype=torch.bool, device=dev)
+    soft = torch.zeros(fb.numel(), dtype=torch.int32, device=dev)      # bit 2 of the re-run steps (pred_cov jitter)
+    for idx in range(H):
+        xh = torch.cat((xd, xd[-1] + dx * torch.arange(1, idx + 1, device=dev)))
+        kw = dict(eps=ep[fb, fs, idx].reshape(-1, 1, 1), mean_kind=mean_kind, k=k, mr_theta=mr_theta,
+                  mr_latent=None if mrl is None else mrl[fb], theta=theta, latent=None if lat is None else lat[fb],
+                  joint=False, jitter=jitter, vol_mode=VOL_SIGMA, check=False)
+        if rh is not None:
+            kw.update(resid_given=rh, mean_test=mt[fb, idx].reshape(-1, 1))
+        o, di, si = rollout(xh, yh, sig, pv[fb, fs, idx].reshape(-1, 1, 1), **kw)
+        o = o.reshape(-1)
+        bad |= (si != 0) | ((di.reshape(-1) & 4) != 0)
+        soft |= di.reshape(-1) & 2
+        res[:, idx] = o
+        yh = torch.cat((yh, o.unsqueeze(-1)), -1)
+        sig = torch.cat((sig, pv[fb, fs, idx].unsqueeze(-1)), -1)
+        if rh is not None:
+            rh = torch.cat((rh, (o - mt[fb, idx]).unsqueeze(-1)), -1)
+    out[fb, fs] = res
+    flags = dinfo[fb, fs]
+    dinfo[fb, fs] = torch.where(bad, flags | 4, soft | 8)              # repaired: the first run's flags no longer apply
 
 
 def rollout_stats(samples, truth=None, strike=None, exp=False):
