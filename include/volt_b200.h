@@ -160,7 +160,9 @@ int volt_mvn_sample(const float* mean, const float* cov, const float* eps, int B
  *   use_theta / theta / latent (B): the rollout-level mean reversion of rollout_utils.py:41-42;
  *   jitter: psd_safe_cholesky jitter (1e-4 in rollout_utils.py:35,46; 1e-6 in VoltMagpie.py:87,92).
  * Outputs samples (B,S,H) log prices; draw_info (B,S) bit flags (1: non-positive pivot in the per-draw rows,
- * 2: pred_cov needed jitter, 4: pred_cov not PSD after 3 tries); series_info (B) cholesky_ex info of the shared block. */
+ * 2: pred_cov needed jitter, 4: pred_cov not PSD after 3 tries); series_info (B) cholesky_ex info of the shared block.
+ * A draw with bit 1 set has to be re-run by the caller as its own series, one step at a time (the reference jitters that
+ * draw's whole matrix, rollout_utils.py:35); volt_b200.ops.rollout does so and marks repaired draws with bit 8. */
 int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mode, const float* pred_vol, const float* eps,
                  int B, int n, int S, int H, int mean_kind, int k, float mr_theta, const float* mr_latent,
                  const float* resid_given, const float* mean_test, int use_theta, float theta, const float* latent, int joint,
