@@ -32,7 +32,9 @@ struct LargeParams {
   float* z;            // (Tp): residual, updated right-looking (r_i -= W[i,j] z_j)
   float* zf;           // (Tp): z = L^-1 r, block j written by CTA 0 of step j
   float* alpha;        // (Tp)
-  float* acc;          // [0] sum log L_ii, [1] tr(A^-1)
+  float* acc;          // [0] sum log L_ii
+  float* trp;          // (nb, trp_ld) per-(step, CTA) partial sums of |L^-1|_F^2, added in a fixed order by the finish kernel
+  int trp_ld;
   float* origd;        // (Tp) original diagonal of A (pivot failure predicate)
   int* flag;           // first failing pivot index, -1 = none
 };
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j
   }
   if (mode) {
     sq = block_sum(sq, c.red);
-    if (tid == 0) atomicAdd(p.acc + 1, sq);
+    if (tid == 0) p.trp[(size_t)j * p.trp_ld + blockIdx.x] = sq;   // one slot per (step, CTA): no atomics, reproducible sum
   }
   cta_teardown(sh);
 }
@@ -306,7 +308,8 @@ __global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int 
 // ---- scalars
 __global__ void __launch_bounds__(256) large_finish_kernel(LargeParams p, float jit_used, float* scalars, float* alpha_out, int* info) {
   __shared__ float red[32];
-  float zz = 0.f, aa = 0.f, ar = 0.f;
+  float zz = 0.f, aa = 0.f, ar = 0.f, trs = 0.f;
+  for (int i = threadIdx.x; i < p.nb * p.trp_ld; i += 256) trs += p.trp[i];
   for (int i = threadIdx.x; i < p.T; i += 256) {
     const float zi = p.zf[i], ai = p.alpha[i];
     zz = fmaf(zi, zi, zz);
@@ -314,9 +317,9 @@ __global__ void __launch_bounds__(256) large_finish_kernel(LargeParams p, float 
     ar = fmaf(ai, p.resid[i], ar);
     if (alpha_out) alpha_out[i] = ai;
   }
-  const float inv_quad = block_sum(zz, red), alal = block_sum(aa, red), alr = block_sum(ar, red);
+  const float inv_quad = block_sum(zz, red), alal = block_sum(aa, red), alr = block_sum(ar, red), tr_sum = block_sum(trs, red);
   if (threadIdx.x == 0) {
-    const float Tf = (float)p.T, logdet = 2.f * p.acc[0], tr = p.acc[1];
+    const float Tf = (float)p.T, logdet = 2.f * p.acc[0], tr = tr_sum;
     scalars[0] = -0.5f * (inv_quad + logdet + Tf * 1.8378770664093453f) / Tf;
     scalars[1] = 0.5f * (alal - tr) / Tf;
     scalars[2] = logdet; scalars[3] = inv_quad; scalars[4] = tr; scalars[5] = alal; scalars[6] = alr; scalars[7] = jit_used;
@@ -342,7 +345,8 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   if (s) return s;
   s = get_workspace(tp2 * sizeof(float), &u, 10);
   if (s) return s;
-  const size_t aux_fl = (size_t)p.nb * NB * NB + 4 * (size_t)p.Tp + 16;
+  p.trp_ld = (p.Tp + CM - 1) / CM + 1;
+  const size_t aux_fl = (size_t)p.nb * NB * NB + 4 * (size_t)p.Tp + 16 + (size_t)p.nb * p.trp_ld;
   s = get_workspace(aux_fl * sizeof(float), &aux, 11);
   if (s) return s;
   p.W = (float*)w;
@@ -354,6 +358,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   p.zf = p.origd + p.Tp;
   p.acc = p.zf + p.Tp;
   p.flag = reinterpret_cast<int*>(p.acc + 4);
+  p.trp = p.acc + 16;
   if (mp.kind == KIND_VOL) p.V = mp.V + (size_t)b * mp.T;
   else if (mp.kind == KIND_BM) { p.V = mp.x; }
   else { p.dense = mp.dense + (size_t)b * mp.dense_bstride; p.ldd = mp.ldd; }
@@ -432,6 +437,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     if (flag < 0 || attempt >= mp.max_tries || !(mp.jitter > 0.f)) break;
     jit_used = mp.jitter * powf(10.f, (float)attempt);
   }
+  VOLT_CUDA(cudaMemsetAsync(p.trp, 0, (size_t)p.nb * p.trp_ld * sizeof(float), st));
   if (mp.do_inverse) {
     bool rest_pending = false;
     for (int k = 0; k < p.nb; ++k) {
