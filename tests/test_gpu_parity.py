@@ -769,3 +769,13 @@ def test_property_random_shapes_cov_and_mll(B, T, seed, raw):
         assert relerr(out["mll"][b], ref["mll"]) < 1e-4
         assert relerr(out["draw_noise"][b], ref["draw_noise"]) < 2e-3
         assert relerr(out["alpha"][b], ref["alpha"]) < 2e-3
+
+
+def test_large_series_path_is_bitwise_reproducible(vb):
+    """The multi-CTA path (T >= 1536) sums tr(A^-1) from per-CTA slots in a fixed order: repeated calls agree bit for bit."""
+    x, vol, logy = O.synth_series(1, 2048)
+    _, resid = vb.ops.ma_mean("ewma", logy.cuda(), 25, want_resid=True)
+    raw = torch.full((1,), 1e-5).cuda()
+    outs = [vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid, raw) for _ in range(3)]
+    for o in outs[1:]:
+        assert torch.equal(o["scalars"], outs[0]["scalars"]) and torch.equal(o["alpha"], outs[0]["alpha"])
