@@ -274,7 +274,11 @@ __global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j
 //   mode 1 (inverse):   A = C = Ut, B = W; rows < row_end (Ut is upper triangular).
 // The host calls it with K = 64 inside a 256-column panel and once with K = 256 for everything to the right of the
 // panel, which cuts the read-modify-write traffic on C by 4x compared with a plain NB = 64 right-looking sweep.
-__global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int mode, int row_lo, int row_end, int col_lo, int col_hi,
+// Three CTAs per SM: 128 TMEM columns, the 32 KB single-buffered stage of the batched kernel's small instance (gemm_tc1) and
+// nothing else in shared memory -- a tile's fixed costs (TMEM allocation, first loads, MMA drain) overlap with the
+// other two resident tiles.
+constexpr size_t UPDATE_SMEM = Y_BYTES + 64;
+__global__ void __launch_bounds__(NT, 3) large_update_kernel(LargeParams p, int mode, int row_lo, int row_end, int col_lo, int col_hi,
                                                              int k_lo, int k_hi) {
   const int ld = p.Tp;
   const int r_base = row_lo + CM * blockIdx.y;      // rows of the C tile
@@ -282,13 +286,28 @@ __global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int 
   if (r_base >= row_end || c_base >= col_hi) return;
   if (!mode && c_base > r_base + CM - 1) return;    // tile entirely above the diagonal
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Shared sh;
-  cta_setup(sh, smem_raw, true);
-  Ctx& c = sh.c;
+  if ((s_u32(smem_raw) & 1023u) != 0u) __trap();
+  Ctx c;
+  c.X = smem_raw;
+  c.bar = reinterpret_cast<uint64_t*>(smem_raw + Y_BYTES);
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(smem_raw + Y_BYTES + 16);
+  c.phase = 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(s_tmem_p)), "n"(T3_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(c.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *s_tmem_p;
   const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
   float* Cm = mode ? p.Ut : p.W;
-  gemm_tc<false>(c, Cm, ld, r_base, row_end, c_base, k_lo, k_hi, nullptr, p.W);
+  gemm_tc1<false>(c, Cm, ld, r_base, row_end, c_base, k_lo, k_hi, nullptr, p.W);
   float s[32];
   tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, s);
   tc_fence_before();
@@ -302,7 +321,9 @@ __global__ void __launch_bounds__(NT, 2) large_update_kernel(LargeParams p, int 
       dst[q] = v;
     }
   }
-  cta_teardown(sh);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(T3_COLS) : "memory");
 }
 
 // ---- scalars
@@ -372,7 +393,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   if (!attr) {
     VOLT_CUDA(cudaFuncSetAttribute(large_diagpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     VOLT_CUDA(cudaFuncSetAttribute(large_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
-    VOLT_CUDA(cudaFuncSetAttribute(large_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
+    VOLT_CUDA(cudaFuncSetAttribute(large_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     attr = true;
   }
   // Look-ahead over two streams.  The deferred K = 256 update of panel P is split by columns: (a) the columns of panel
@@ -392,7 +413,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
     if (nrow <= 0 || ncol <= 0) return;
     dim3 grid(ncol, nrow);
-    large_update_kernel<<<grid, NT, LARGE_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
+    large_update_kernel<<<grid, NT, UPDATE_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
   };
   // deferred update of the panel ending at `panel_end`: part (a) on st after the previous part (b) has left the tiles,
   // part (b) on sb once the panel is final

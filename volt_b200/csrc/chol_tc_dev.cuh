@@ -305,7 +305,9 @@ constexpr uint32_t Y_L_OFF = Y_BYTES, Y_CT_OFF = Y_L_OFF, Y_VEC_OFF = Y_L_OFF + 
 static_assert(Y_TMP + DIAG2_SCRATCH_FLOATS * 4 <= Y_BYTES, "diag scratch must fit the stage region");
 
 template <bool PHASE_B>
-__device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_end, int b_row0, int k_lo, int k_hi, const float* dinv) {
+__device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_end, int b_row0, int k_lo, int k_hi, const float* dinv,
+                         const float* SB = nullptr) {
+  if (SB == nullptr) SB = S;  // B operand rows from a second matrix (large-matrix inverse sweep)
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int nk = (k_hi - k_lo) / 32;
   if (nk <= 0) return false;
@@ -319,7 +321,7 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
-      rb[i] = *reinterpret_cast<const float4*>(S + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
+      rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
     }
   };
   auto gload_a = [&](int k0) {
