@@ -281,10 +281,7 @@ constexpr size_t UPDATE_SMEM = Y_BYTES + 64;
 __global__ void __launch_bounds__(NT, 3) large_update_kernel(LargeParams p, int mode, int row_lo, int row_end, int col_lo, int col_hi,
                                                              int k_lo, int k_hi) {
   const int ld = p.Tp;
-  const int r_base = row_lo + CM * blockIdx.y;      // rows of the C tile
-  const int c_base = col_lo + NB * blockIdx.x;      // columns of the C tile
-  if (r_base >= row_end || c_base >= col_hi) return;
-  if (!mode && c_base > r_base + CM - 1) return;    // tile entirely above the diagonal
+  const int ncol = (col_hi - col_lo) / NB, nrow = (row_end - row_lo + CM - 1) / CM;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((s_u32(smem_raw) & 1023u) != 0u) __trap();
   Ctx c;
@@ -307,19 +304,26 @@ __global__ void __launch_bounds__(NT, 3) large_update_kernel(LargeParams p, int 
   c.tmem = *s_tmem_p;
   const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
   float* Cm = mode ? p.Ut : p.W;
-  gemm_tc1<false>(c, Cm, ld, r_base, row_end, c_base, k_lo, k_hi, nullptr, p.W);
-  float s[32];
-  tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, s);
-  tc_fence_before();
-  const int gr = r_base + row;
-  if (gr < row_end) {
-    float4* dst = reinterpret_cast<float4*>(Cm + (size_t)gr * ld + c_base + c0);
+  // persistent over the launch's tiles (row-major within a tile row so that neighbouring CTAs share the A panel rows)
+  for (int t = blockIdx.x; t < ncol * nrow; t += gridDim.x) {
+    const int r_base = row_lo + CM * (t / ncol);      // rows of the C tile
+    const int c_base = col_lo + NB * (t % ncol);      // columns of the C tile
+    if (!mode && c_base > r_base + CM - 1) continue;  // tile entirely above the diagonal
+    gemm_tc1<false>(c, Cm, ld, r_base, row_end, c_base, k_lo, k_hi, nullptr, p.W);
+    float s[32];
+    tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, s);
+    tc_fence_before();
+    const int gr = r_base + row;
+    if (gr < row_end) {
+      float4* dst = reinterpret_cast<float4*>(Cm + (size_t)gr * ld + c_base + c0);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 v = dst[q];
-      v.x -= s[4 * q]; v.y -= s[4 * q + 1]; v.z -= s[4 * q + 2]; v.w -= s[4 * q + 3];
-      dst[q] = v;
+      for (int q = 0; q < 8; ++q) {
+        float4 v = dst[q];
+        v.x -= s[4 * q]; v.y -= s[4 * q + 1]; v.z -= s[4 * q + 2]; v.w -= s[4 * q + 3];
+        dst[q] = v;
+      }
     }
+    __syncthreads();   // every thread has read its accumulator row before the next tile's first MMA overwrites it
   }
   tc_fence_before();
   __syncthreads();
@@ -412,7 +416,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   auto update = [&](cudaStream_t s2, int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
     const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
     if (nrow <= 0 || ncol <= 0) return;
-    dim3 grid(ncol, nrow);
+    const int grid = min(ncol * nrow, 3 * sm_count());
     large_update_kernel<<<grid, NT, UPDATE_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
   };
   // deferred update of the panel ending at `panel_end`: part (a) on st after the previous part (b) has left the tiles,
