@@ -256,9 +256,20 @@ __device__ __forceinline__ void dot2x2(const float* a0, const float* a1, const f
 constexpr int XT_LD = 52;
 constexpr int DIAG3_SCRATCH_FLOATS = 4 * 16 * I16_LD + 16 * XT_LD + 48 * 20;
 
+// -DVOLT_PROFILE: clock64() deltas of the pivot warp's thread 0 in CTA 0 per sub-phase (read by tools/seg_probe.py)
+#ifdef VOLT_PROFILE
+static __device__ long long g_diag_prof[8];
+#define DTICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _n = clock64(); g_diag_prof[i] += _n - dlast; dlast = _n; } } while (0)
+#else
+#define DTICK(i) do { } while (0)
+#endif
+
 template <int RLD>
 __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* diagl, const float* origd, int* flag, int col0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef VOLT_PROFILE
+  long long dlast = clock64();
+#endif
   float* I16 = scratch;                          // 4 x (16 x I16_LD): row-major inverses of the pivot blocks
   float* XT = scratch + 4 * 16 * I16_LD;         // 16 x XT_LD: solved panel, transposed (XT[t][row] = X[row][t])
   float* WT = XT + 16 * XT_LD;                   // 48 x 20: per inverse block (16 x 20), WT[c][k] = W[k][c]
@@ -275,7 +286,9 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
         if ((k >> 4) != (cc >> 4)) LiT[k * RLD + cc] = 0.f;   // diagonal 16-blocks are written by the pivot warps
       }
     }
+    DTICK(0);
     __syncthreads();
+    DTICK(1);
     if (R > 0) {
       // ---- P2: panel solve X = S_panel Linv16^T, 16-row groups x (2 x 2 tiles); result kept transposed in XT
       if (tid < R * 4) {
@@ -288,6 +301,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
         XT[tj * XT_LD + r0 + 8] = x10; XT[(tj + 8) * XT_LD + r0 + 8] = x11;
       }
       __syncthreads();
+      DTICK(2);
       // ---- P3: write the panel back (row fastest) and apply the trailing update D[r][c] -= X[r].X[c] in 4 x 4 tiles
       //      that touch the lower triangle (the strictly-upper entries a diagonal tile also updates are never read)
       if (tid < R * 4) {
@@ -323,6 +337,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
         }
       }
       __syncthreads();
+      DTICK(3);
     }
   }
   if (tid == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
@@ -351,6 +366,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
     }
     __syncthreads();
   }
+  DTICK(4);
 }
 
 // ---------------------------------------------------------------------------------------------- generator

@@ -359,7 +359,10 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
 
 #ifdef VOLT_PROFILE
   TICK(11);
-  if (tid == 0 && blockIdx.x == 0 && p.z_out == nullptr && p.alpha) for (int i = 0; i < 12; ++i) p.alpha[i] = (float)seg[i];
+  if (tid == 0 && blockIdx.x == 0 && p.z_out == nullptr && p.alpha) {
+    for (int i = 0; i < 12; ++i) p.alpha[i] = (float)seg[i];
+    for (int i = 0; i < 8; ++i) { p.alpha[12 + i] = (float)g_diag_prof[i]; g_diag_prof[i] = 0; }
+  }
 #endif
   tc_fence_before();
   __syncthreads();
