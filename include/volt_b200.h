@@ -16,6 +16,8 @@
  *   - return value: 0 on success, <0 on error (VOLT_ERR_*); volt_last_error() returns the message.
  *     Numerical failure (matrix not positive definite) is NOT an error return: it is reported per matrix in `info`
  *     exactly like torch.linalg.cholesky_ex (1-based order of the first non-positive leading minor, 0 = success).
+ *   - an empty batch (B == 0 / S == 0 series) is a successful no-op for every batched entry point: no pointer is
+ *     dereferenced and nothing is launched (empty shards of a small job); negative sizes are argument errors.
  *   - requires an sm_100 device; there is no CPU fallback.
  */
 #ifndef VOLT_B200_H_

@@ -178,6 +178,7 @@ int volt_set_mll_impl(int impl) {
 }
 
 int volt_cumtrapz(const float* x, int x_batched, const float* y, int B, int T, int vol_mode, int half_last, float* V, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && y && V, "volt_cumtrapz: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_cumtrapz: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
   VOLT_REQUIRE(vol_mode >= 0 && vol_mode <= 2, "volt_cumtrapz: bad vol_mode %d", vol_mode);
@@ -186,6 +187,7 @@ int volt_cumtrapz(const float* x, int x_batched, const float* y, int B, int T, i
 
 int volt_vol_cov(const float* x, int x_batched, const float* vol, int vol_mode, int B, int T, const float* add_diag, int add_stride,
                  float* K, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && vol && K, "volt_vol_cov: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_vol_cov: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
   void* V = nullptr;
@@ -203,6 +205,7 @@ int volt_bm_cov(const float* x1, int n1, const float* x2, int n2, const float* v
 }
 
 int volt_ewma(const float* y, int S, int T, int k, float* out, void* stream) {
+  if (S == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(y && out, "volt_ewma: null pointer");
   VOLT_REQUIRE(S >= 1 && T >= 1 && k >= 1, "volt_ewma: need S,T,k >= 1 (got %d,%d,%d)", S, T, k);
   void* w = nullptr;
@@ -215,6 +218,7 @@ int volt_ewma(const float* y, int S, int T, int k, float* out, void* stream) {
 
 int volt_ma_mean(const float* y, int S, int T, int k, int kind, float theta, const float* latent, float* out, float* e_out,
                  float* ee_out, float* resid_out, void* stream) {
+  if (S == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(y && out, "volt_ma_mean: null pointer");
   VOLT_REQUIRE(S >= 1 && T >= 1 && k >= 1, "volt_ma_mean: need S,T,k >= 1 (got %d,%d,%d)", S, T, k);
   VOLT_REQUIRE(kind >= VOLT_MA_EWMA && kind <= VOLT_MA_MEANREVERT, "volt_ma_mean: bad kind %d", kind);
@@ -230,6 +234,7 @@ int volt_ma_mean(const float* y, int S, int T, int k, int kind, float theta, con
 int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* noise,
                       int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
                       void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && vol && resid && scalars, "volt_mll_grad_vol: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
   void* V = nullptr;
@@ -245,6 +250,7 @@ int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_m
 
 int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise, int noise_stride,
                      int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && scale && resid && scalars, "volt_mll_grad_bm: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1, "volt_mll_grad_bm: need B,T >= 1");
   MllParams p = base_params(B, T, resid, noise, noise_stride, jitter, max_tries, scalars, alpha, info);
@@ -258,6 +264,7 @@ int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const
 int volt_mll_grad_bm_inv(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise, int noise_stride,
                          int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, float* linv_t,
                          void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && scale && resid && scalars && linv_t, "volt_mll_grad_bm_inv: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1, "volt_mll_grad_bm_inv: need B,T >= 1");
   VOLT_REQUIRE(g_mll_impl, "volt_mll_grad_bm_inv: needs the tensor-core implementation (VOLT_MLL_IMPL=tc)");
@@ -272,6 +279,7 @@ int volt_mll_grad_bm_inv(const float* x, const float* scale, int scale_stride, c
 
 int volt_mll_grad_dense(const float* K, long long k_bstride, int ld, const float* resid, const float* noise, int noise_stride, int B,
                         int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(K && resid && scalars, "volt_mll_grad_dense: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1 && ld >= T, "volt_mll_grad_dense: bad shape");
   MllParams p = base_params(B, T, resid, noise, noise_stride, jitter, max_tries, scalars, alpha, info);
@@ -284,6 +292,7 @@ int volt_mll_grad_dense(const float* K, long long k_bstride, int ld, const float
 
 int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid, const float* noise, int noise_stride, int B, int T,
                            float jitter, int max_tries, float* scalars, float* alpha, int* info) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && vol && resid && noise && scalars, "volt_mll_grad_vol_host: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol_host: need B >= 1 and T >= 2");
   const size_t bt = (size_t)B * T;
@@ -350,6 +359,7 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
 
 int volt_potrf(const float* A, long long a_bstride, int lda, const float* add_diag, int add_stride, int B, int T, float jitter,
                int max_tries, float* L, long long l_bstride, int ldl, float* jitter_used, int* info, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(A && L, "volt_potrf: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1 && lda >= T && ldl >= T, "volt_potrf: bad shape");
   void* sc = nullptr;
@@ -371,6 +381,7 @@ int volt_potrf(const float* A, long long a_bstride, int lda, const float* add_di
 
 int volt_potrs(const float* L, long long l_bstride, int ldl, int B, int T, float* rhs, long long r_bstride, int nrhs,
                int forward_only, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(L && rhs, "volt_potrs: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1 && nrhs >= 1 && ldl >= T, "volt_potrs: bad shape");
   return launch_chol_solve(L, l_bstride, ldl, B, T, rhs, r_bstride, nrhs, forward_only ? 1 : 0, ST(stream));
@@ -378,6 +389,7 @@ int volt_potrs(const float* L, long long l_bstride, int ldl, int B, int T, float
 
 int volt_bmgp_posterior(const float* x, const float* y, int B, int T, const float* xs, int H, const float* vol, int vol_stride,
                         const float* noise, int noise_stride, float* mean, float* cov, int* info, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && y && xs && vol && noise && mean && cov, "volt_bmgp_posterior: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1 && H >= 1, "volt_bmgp_posterior: bad shape");
   const size_t wfl = (size_t)B * T * (H + 1) + (size_t)B * H * H + (size_t)B * H + (size_t)B * VOLT_NSCALARS;
@@ -410,6 +422,7 @@ int volt_bmgp_posterior(const float* x, const float* y, int B, int T, const floa
 
 int volt_mvn_sample(const float* mean, const float* cov, const float* eps, int B, int H, int S, float jitter, int exp_out,
                     float* samples, int* info, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(mean && cov && eps && samples, "volt_mvn_sample: null pointer");
   VOLT_REQUIRE(B >= 1 && H >= 1 && S >= 1, "volt_mvn_sample: bad shape");
   void* Lc = nullptr;
@@ -424,6 +437,7 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
                  int n, int S, int H, int mean_kind, int k, float mr_theta, const float* mr_latent, const float* resid_given,
                  const float* mean_test, int use_theta, float theta, const float* latent, int joint, float jitter,
                  unsigned long long seed, float* samples, int* draw_info, int* series_info, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(x && logy && vol && pred_vol && samples, "volt_rollout: null pointer");
   VOLT_REQUIRE(B >= 1 && n >= 2 && S >= 1 && H >= 1, "volt_rollout: bad shape (B=%d n=%d S=%d H=%d)", B, n, S, H);
   VOLT_REQUIRE(mean_kind >= VOLT_MA_EWMA && mean_kind <= VOLT_MA_GIVEN, "volt_rollout: bad mean_kind %d", mean_kind);
@@ -494,6 +508,7 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
 
 int volt_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag,
                        float* ecdf, float* mean, float* sd, float* nll, float* payoff, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(samples, "volt_rollout_stats: null samples");
   VOLT_REQUIRE(B >= 1 && S >= 1 && H >= 1, "volt_rollout_stats: need B, S, H >= 1 (got %d, %d, %d)", B, S, H);
   VOLT_REQUIRE(!nll || truth, "volt_rollout_stats: nll needs truth");
@@ -504,6 +519,7 @@ int volt_rollout_stats(const float* samples, int B, int S, int H, const float* t
 
 int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t,
                    const float* gh_w, int nq, int B, int n, float inv_n, float* grad_chol, float* rows, void* stream) {
+  if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do
   VOLT_REQUIRE(chol_var && W && var_mean && y && gh_t && gh_w && grad_chol && rows, "volt_gpcv_rows: null pointer");
   VOLT_REQUIRE(B >= 1 && n >= 1 && nq >= 1 && nq <= 128, "volt_gpcv_rows: need B, n >= 1 and 1 <= nq <= 128 (got %d, %d, %d)", B, n, nq);
   return launch_gpcv_rows(chol_var, W, var_mean, y, gh_t, gh_w, nq, B, n, inv_n, grad_chol, rows, ST(stream));
