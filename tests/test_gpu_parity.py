@@ -354,6 +354,32 @@ def test_rollout_philox_statistics(vb):
     assert abs(float(z.mean())) < 0.08 and abs(float(z.std()) - 1.0) < 0.08
 
 
+def test_rollout_philox_every_step_is_standard_normal_and_independent(vb):
+    """One Philox block feeds four horizon steps (both Box-Muller outputs of both pairs).  With a given zero mean and a
+    constant predicted volatility the noise-free predictor is sample_h = sample_{h-1} + sqrt(dx/2) sigma eps_h (KAT-3), so
+    the base normals of EVERY step can be read back from the increments: unit variance, zero mean, no correlation
+    between steps (inside and across Philox blocks), different draws / series / seeds differ."""
+    n, S, H = 64, 8192, 10
+    x, vol, logy = O.synth_series(2, n, seed=8)
+    sig = vol[:, -1]
+    pred_vol = sig[:, None, None].expand(2, S, H).contiguous()
+    zero = torch.zeros(2, H)
+    out, _, _ = vb.ops.rollout(x, logy, vol, pred_vol, eps=None, mean_kind="given", resid_given=logy, mean_test=zero, seed=77)
+    out = out.cpu().double()
+    prev = torch.cat([logy[:, None, -1:].expand(2, S, 1).double(), out[:, :, :-1]], -1)
+    z = (out - prev) / ((0.5 * x[1]).sqrt().double() * sig.double())[:, None, None]      # (2, S, H) base normals
+    assert float(z.mean(1).abs().max()) < 0.05
+    assert float((z.std(1) - 1.0).abs().max()) < 0.04
+    for b in range(2):
+        c = torch.corrcoef(z[b].T)
+        assert float((c - torch.eye(H, dtype=c.dtype)).abs().max()) < 0.05
+    assert float(torch.corrcoef(torch.stack([z[0, :, 0], z[1, :, 0]]))[0, 1].abs()) < 0.05   # series differ
+    kurt = float(((z - z.mean(1, keepdim=True)) ** 4).mean() / z.var(1).mean() ** 2)
+    assert abs(kurt - 3.0) < 0.15
+    out2, _, _ = vb.ops.rollout(x, logy, vol, pred_vol, eps=None, mean_kind="given", resid_given=logy, mean_test=zero, seed=78)
+    assert not torch.equal(out2.cpu().double(), out)
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_c2_properties(vb):
     """BASELINE config 2 (1024 series x T=512): spot-check series against the oracle, finite everywhere, and the

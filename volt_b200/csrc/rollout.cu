@@ -90,6 +90,29 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// four standard normals from ONE Philox4x32-10 block (both Box-Muller outputs of both uniform pairs): the autoregressive
+// rollout draws one block per four horizon steps (counter = (series, draw, idx / 4)), a quarter of the generator work
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, uint32_t a, uint32_t b, uint32_t c3, float (&z)[4]) {
+  uint32_t c[4] = {a, b, c3, 0x5eed4u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+    const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.f * logf(u1));
+    float sn, cs;
+    sincospif(2.f * u2, &sn, &cs);
+    z[2 * h] = rad * cs;
+    z[2 * h + 1] = rad * sn;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- rollout
 // value of a grown per-draw series at absolute index j: shared part (tail kept in smem) or the draw's own history
 __device__ __forceinline__ float grown_at(int j, int nsh, const float* tail, int tail_len, float first, const float* hist) {
@@ -195,6 +218,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
       double accV = (double)Vn1;   // trapezoid integral up to the last conditioning point
       float F2 = 0.f, FW = 0.f, FQ = 0.f, QW = 0.f, QQ = 0.f;
       float r_prev = 0.f;          // residual y - mean of the most recently appended point
+      float zq[4] = {0.f, 0.f, 0.f, 0.f};   // in-kernel normals: one Philox block per four steps
       for (int idx = 0; idx < H; ++idx) {
         const int m = n + idx;     // number of conditioning points at this step
         const float pvi = pv[idx];
@@ -259,7 +283,14 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
           if (tries == 3) flags |= 4;
           cov = c2;
         }
-        const float e_n = p.eps ? ep[idx] : philox_normal(p.seed, (uint32_t)b, (uint32_t)s, (uint32_t)idx);
+        float e_n;
+        if (p.eps) {
+          e_n = ep[idx];
+        } else {
+          if ((idx & 3) == 0) philox_normal4(p.seed, (uint32_t)b, (uint32_t)s, (uint32_t)(idx >> 2), zq);
+          const int sel = idx & 3;
+          e_n = sel == 0 ? zq[0] : sel == 1 ? zq[1] : sel == 2 ? zq[2] : zq[3];
+        }
         const float sample = fmaf(sqrtf(cov), e_n, mean);
         out[idx] = sample;
         r_prev = sample - m_test;
