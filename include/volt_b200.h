@@ -126,7 +126,10 @@ int volt_mll_grad_bm_inv(const float* x, const float* scale, int scale_stride, c
 int volt_mll_grad_dense(const float* K, long long k_bstride, int ld, const float* resid, const float* noise, int noise_stride,
                         int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info, void* stream);
 
-/* Host-buffer variant of volt_mll_grad_vol (all pointers are HOST memory; pinned memory recommended). */
+/* Host-buffer variant of volt_mll_grad_vol (all pointers are HOST memory; pinned memory recommended).  Synchronous: the
+ * outputs are valid on return.  The copies are inside the call: for a large batch the inputs of the first series are
+ * copied, ONE kernel is launched for the whole batch, and the remaining inputs follow on a copy stream underneath it
+ * (later series wait in-kernel for an arrival flag written by the copy engine); the CumTrapz prefix is built in-kernel. */
 int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid, const float* noise, int noise_stride, int B,
                            int T, float jitter, int max_tries, float* scalars, float* alpha, int* info);
 

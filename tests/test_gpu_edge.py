@@ -134,3 +134,26 @@ def test_kernel_protocol_diag_and_shapes(vb):
     assert torch.equal(d.cpu().reshape(-1), O.vol_kernel(x, vol[0], diag=True))
     Kb = k(x.cuda().expand(2, T).unsqueeze(-1), vol.cuda().unsqueeze(-1)).evaluate().cpu()
     assert torch.equal(Kb, O.vol_kernel(x, vol))
+
+
+@pytest.mark.parametrize("B,T,pinned", [(700, 64, True), (1024, 128, False), (400, 96, True), (300, 100, True), (5, 512, False),
+                                         (1, 2048, True)])
+def test_host_buffer_entry_equals_device_entry(vb, B, T, pinned):
+    """volt_mll_grad_vol_host (host pointers, copies inside the call; for large batches one kernel launch whose later
+    series wait for an arrival flag while their inputs are still being copied) == the device-pointer entry, bit for bit."""
+    lib = vb._lib.load()
+    x, vol, logy = vb.batched.synth_series(B, T)
+    resid = (logy - logy.mean(-1, keepdim=True)).contiguous()
+    noise = torch.linspace(0.05, 1.5, B)
+    ref = vb.ops.mll_grad("vol", x.cuda(), vol.cuda(), resid.cuda(), noise.cuda(), check=False)
+    torch.cuda.synchronize()
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    hx, hv, hr, hn = pin(x.contiguous()), pin(vol.contiguous()), pin(resid), pin(noise)
+    hs, ha, hi = pin(torch.empty(B, 16)), pin(torch.empty(B, T)), pin(torch.empty(B, dtype=torch.int32))
+    for _ in range(3):   # repeated calls reuse the staging buffers and the flag
+        hs.zero_(); ha.zero_()
+        vb._lib.check(lib.volt_mll_grad_vol_host(hx.data_ptr(), hv.data_ptr(), hr.data_ptr(), hn.data_ptr(), 1, B, T, 1e-6, 3,
+                                                  hs.data_ptr(), ha.data_ptr(), hi.data_ptr()), "volt_mll_grad_vol_host")
+        assert torch.equal(hs[:, :8], ref["scalars"][:, :8].cpu())
+        assert torch.equal(ha, ref["alpha"].cpu())
+        assert int(hi.abs().sum()) == 0

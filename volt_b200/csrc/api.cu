@@ -31,7 +31,7 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 // ---- per-device cached workspaces
-constexpr int kSlots = 12;
+constexpr int kSlots = 13;
 struct Ws {
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -309,45 +309,72 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   float* d_scal = d_noise + n_noise;
   float* d_alpha = d_scal + (size_t)B * VOLT_NSCALARS;
   int* d_info = (int*)(d_alpha + bt);
-  // Two-stage pipeline: the first wave of series (one per resident CTA slot) is copied and launched first, the copy of
-  // the remaining series overlaps its factorisation on a second stream.  Kernels stay on one stream (shared workspace).
+  // Pipeline: the inputs of the first `B0` series are copied and ONE kernel is launched for the whole batch; the copy of
+  // the remaining series runs on the copy stream underneath it, followed by a 4-byte flag.  The persistent CTAs take
+  // series b, b + grid, ... in order and wait for the flag before touching a series >= B0 (by the time a CTA gets
+  // there the data has long arrived).  The flag is written by the copy engine, so it cannot depend on an SM the
+  // waiting CTAs hold.  The prefix sums (CumTrapz) are built inside the kernel: no second launch, no second tail.
   static cudaStream_t s_copy = nullptr, s_comp = nullptr;
-  static cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static cudaEvent_t ev0 = nullptr;
+  static int* h_flags = nullptr;   // pinned {0, 1}
   if (!s_copy) {
     VOLT_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
     VOLT_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     VOLT_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
-    VOLT_CUDA(cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
+    VOLT_CUDA(cudaHostAlloc(&h_flags, 2 * sizeof(int), cudaHostAllocDefault));
+    h_flags[0] = 0;
+    h_flags[1] = 1;
   }
-  void* vres = nullptr;
-  s = get_workspace(bt * sizeof(float), &vres, 1);   // reserve the prefix-sum buffer at full size (no regrow mid-pipeline)
+  void* vflag = nullptr;
+  s = get_workspace(128, &vflag, 12);
   if (s) return s;
-  // first chunk: VOLT_E2E_CHUNK0 series (developer knob), default two series per SM -- large enough to keep the GPU busy while
-  // the rest is copied, small enough that its own copy (the only exposed one) stays short
+  int* d_flag = (int*)vflag;
+  if (g_mll_impl < 0) {
+    const char* e = getenv("VOLT_MLL_IMPL");
+    g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
+  }
+  // first chunk: VOLT_E2E_CHUNK0 series (developer knob), default one series per SM: the CTAs that own three series of a
+  // c2-sized batch are the first ones to be scheduled, and they are the critical path.  Gating needs whole cache lines
+  // per series (T % 32 == 0: a line shared by a copied and a not-yet-copied series could be cached stale) and the
+  // batched tensor-core kernel (not the multi-CTA path for a few very long series, not the SIMT kernel).
   static const int chunk0_env = [] { const char* e = getenv("VOLT_E2E_CHUNK0"); return e ? atoi(e) : 0; }();
-  const int slots = chunk0_env > 0 ? chunk0_env : 2 * sm_count();
-  const int B0 = (B >= 2 * slots && B >= 2 * mll_tc_resident_ctas(T, 0)) ? slots : B;
+  const int slots = chunk0_env > 0 ? chunk0_env : sm_count();
+  const bool batched_tc = g_mll_impl && !(T >= 1536 && B <= 16);
+  const bool gated = batched_tc && (T % 32 == 0) && B >= 2 * slots;
+  const int B0 = gated ? slots : B;
   const size_t n0 = (size_t)B0 * T;
+  VOLT_CUDA(cudaMemcpyAsync(d_flag, h_flags, sizeof(int), cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_noise, noise, n_noise * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_vol, vol, n0 * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_res, resid, n0 * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaEventRecord(ev0, s_copy));
-  if (B0 < B) {
-    VOLT_CUDA(cudaMemcpyAsync(d_vol + n0, vol + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy));
-    VOLT_CUDA(cudaMemcpyAsync(d_res + n0, resid + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy));
-    VOLT_CUDA(cudaEventRecord(ev1, s_copy));
-  }
   VOLT_CUDA(cudaStreamWaitEvent(s_comp, ev0, 0));
-  s = volt_mll_grad_vol(d_x, 0, d_vol, VOLT_VOL_SIGMA, d_res, d_noise, noise_stride, B0, T, jitter, max_tries, d_scal,
-                        alpha ? d_alpha : nullptr, d_info, s_comp);
+  if (batched_tc) {
+    MllParams p = base_params(B, T, d_res, d_noise, noise_stride, jitter, max_tries, d_scal, alpha ? d_alpha : nullptr, d_info);
+    p.kind = KIND_VOL;
+    p.vol_in = d_vol;
+    p.x_in = d_x;
+    p.x_batched = 0;
+    p.vol_mode = VOLT_VOL_SIGMA;
+    p.ready = gated ? d_flag : nullptr;
+    p.ready_from = B0;
+    s = launch_mll_batched_tc(p, s_comp);
+  } else {
+    s = volt_mll_grad_vol(d_x, 0, d_vol, VOLT_VOL_SIGMA, d_res, d_noise, noise_stride, B, T, jitter, max_tries, d_scal,
+                          alpha ? d_alpha : nullptr, d_info, s_comp);
+  }
   if (s) return s;
-  if (B0 < B) {
-    VOLT_CUDA(cudaStreamWaitEvent(s_comp, ev1, 0));
-    s = volt_mll_grad_vol(d_x, 0, d_vol + n0, VOLT_VOL_SIGMA, d_res + n0, d_noise + (noise_stride ? (size_t)B0 * noise_stride : 0),
-                          noise_stride, B - B0, T, jitter, max_tries, d_scal + (size_t)B0 * VOLT_NSCALARS,
-                          alpha ? d_alpha + n0 : nullptr, d_info + B0, s_comp);
-    if (s) return s;
+  if (gated) {   // submitted after the launch: the kernel does not wait for the host to queue these
+    const cudaError_t e1 = cudaMemcpyAsync(d_vol + n0, vol + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy);
+    const cudaError_t e2 = cudaMemcpyAsync(d_res + n0, resid + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy);
+    // the flag must be raised whatever happened above: CTAs are waiting for it (they also give up after ~2 s and trap)
+    cudaError_t e3 = cudaMemcpyAsync(d_flag, h_flags + 1, sizeof(int), cudaMemcpyHostToDevice, s_copy);
+    if (e3 != cudaSuccess) e3 = cudaMemcpy(d_flag, h_flags + 1, sizeof(int), cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+      cudaStreamSynchronize(s_comp);
+      return check_cuda(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "volt_mll_grad_vol_host: copy of the later series");
+    }
   }
   cudaStream_t st = s_comp;
   VOLT_CUDA(cudaMemcpyAsync(scalars, d_scal, (size_t)B * VOLT_NSCALARS * 4, cudaMemcpyDeviceToHost, st));

@@ -31,7 +31,14 @@ namespace tc {
 
 // TRI = true: three CTAs per SM (128 TMEM columns, ~71 KB shared memory, single-buffered stages; chol_tc_dev.cuh);
 // TRI = false: two CTAs per SM with double-buffered stages (series too long for the small shared-memory map).
-template <bool TRI>
+// HOSTIN = true: the instance behind volt_mll_grad_vol_host -- prefix sums built in-kernel from the raw volatility path and
+// an arrival flag for series whose inputs are still being copied (params.cuh); kept out of the device-pointer instance,
+// whose register allocation it would disturb (measured: +2 % on the c2 kernel time when compiled in unconditionally).
+static __device__ __noinline__ void cumtrapz_to_smem(const float* xs, const float* vs, int T, int mode, float* out, int lane) {
+  cumtrapz_warp(xs, vs, T, mode, 1, out, lane);
+}
+
+template <bool TRI, bool HOSTIN = false>
 __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllParams p) {
   constexpr uint32_t LOFF = TRI ? Y_L_OFF : L_OFF, CTOFF = TRI ? Y_CT_OFF : CT_OFF, VECOFF = TRI ? Y_VEC_OFF : VEC_OFF;
   constexpr uint32_t XTMP = TRI ? Y_TMP : X_TMP, TCOLS = TRI ? T3_COLS : TM_COLS;
@@ -85,13 +92,33 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   long long tlast = clock64();
 #endif
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    for (int i = tid; i < Tp; i += NT) {
-      float v = 0.f;
-      if (i < T) {
-        if (p.kind == KIND_VOL) v = p.V[(size_t)b * T + i];
-        else if (p.kind == KIND_BM) v = p.x[i];
+    if (HOSTIN && p.ready && b >= p.ready_from) {
+      // host-buffer entry: this series' inputs were still being copied when the kernel was launched; the copy stream
+      // writes the flag after them (pure DMA, so it cannot wait for an SM that this CTA is holding)
+      if (tid == 0) {
+        int f;
+        for (long long spins = 0;; ++spins) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.ready) : "memory");
+          if (f != 0) break;
+          if (spins > (1ll << 23)) __trap();   // ~2 s: the copy stream died; fail the launch instead of hanging the GPU
+          __nanosleep(200);
+        }
       }
-      c.Vs[i] = v;
+      __syncthreads();
+    }
+    if (HOSTIN && p.kind == KIND_VOL && p.vol_in) {
+      if (warp == 0)
+        cumtrapz_to_smem(p.x_in + (p.x_batched ? (size_t)b * T : 0), p.vol_in + (size_t)b * T, T, p.vol_mode, c.Vs, lane);
+      for (int i = T + tid; i < Tp; i += NT) c.Vs[i] = 0.f;
+    } else {
+      for (int i = tid; i < Tp; i += NT) {
+        float v = 0.f;
+        if (i < T) {
+          if (p.kind == KIND_VOL) v = p.V[(size_t)b * T + i];
+          else if (p.kind == KIND_BM) v = p.x[i];
+        }
+        c.Vs[i] = v;
+      }
     }
     const float sc = (p.kind == KIND_BM) ? p.scale[(size_t)b * p.scale_stride] : 1.f;
     const float dadd0 = p.diag_add ? p.diag_add[(size_t)b * p.diag_stride] : 0.f;
@@ -371,11 +398,11 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
 
 }  // namespace tc
 
-template <bool TRI>
+template <bool TRI, bool HOSTIN>
 static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel<TRI, HOSTIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(mll_batched_tc_kernel)");
     if (s) return s;
     attr_smem = smem;
@@ -389,7 +416,7 @@ static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   if (s) return s;
   p.scratch = reinterpret_cast<float*>(ws);
   p.dinv = p.scratch + (size_t)grid * p.Tp * p.Tp;
-  tc::mll_batched_tc_kernel<TRI><<<grid, NT, smem, st>>>(p);
+  tc::mll_batched_tc_kernel<TRI, HOSTIN><<<grid, NT, smem, st>>>(p);
   return check_cuda(cudaGetLastError(), "mll_batched_tc_kernel");
 }
 
@@ -413,7 +440,9 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   // double-buffered two-CTA kernel (A/B timing)
   static const int force2 = [] { const char* e = getenv("VOLT_TC_CTAS"); return (e && e[0] == '2') ? 1 : 0; }();
   const size_t smem3 = tc::Y_VEC_OFF + vec;
-  if (!force2 && 3 * (smem3 + smem_cta_reserved) <= smem_total) return launch_tc<true>(p, st, smem3, 3);
+  const bool hostin = (p.vol_in != nullptr);
+  if (!force2 && 3 * (smem3 + smem_cta_reserved) <= smem_total)
+    return hostin ? launch_tc<true, true>(p, st, smem3, 3) : launch_tc<true, false>(p, st, smem3, 3);
   const size_t smem = tc::VEC_OFF + vec;
   if (smem > 227 * 1024) {
     set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);
@@ -422,7 +451,7 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   int per_sm = (int)(smem_total / (smem + smem_cta_reserved));
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
-  return launch_tc<false>(p, st, smem, per_sm);
+  return hostin ? launch_tc<false, true>(p, st, smem, per_sm) : launch_tc<false, false>(p, st, smem, per_sm);
 }
 
 }  // namespace volt

@@ -9,47 +9,13 @@
 namespace volt {
 
 // ------------------------------------------------------------------------------------------ cumtrapz
-// One warp per series.  torch.cumsum on CPU accumulates float32 data in a double accumulator and
-// rounds each prefix to float32; we do the same (per-lane sequential double sums + a warp scan of
-// the lane totals), so the result equals the reference's to the last bit except for double-rounding ties.
+// One warp per series (cumtrapz_warp, params.cuh).
 __global__ void cumtrapz_kernel(const float* __restrict__ x, int x_batched, const float* __restrict__ vol,
                                 int B, int T, int mode, int half_last, float* __restrict__ V) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
-  const float* xs = x + (x_batched ? (size_t)warp * T : 0);
-  const float* vs = vol + (size_t)warp * T;
-  float* out = V + (size_t)warp * T;
-  const float dx = xs[1] - xs[0];
-  const float w_end = dx * 0.5f;
-  const int seg = (T + 31) / 32;
-  const int lo = min(lane * seg, T), hi = min(lo + seg, T);
-  double s = 0.0;
-  for (int i = lo; i < hi; ++i) {
-    float v = vs[i];
-    if (mode == 2) v = expf(v);
-    const float y = mode ? v * v : v;
-    float w = (i == 0 || (half_last && i == T - 1)) ? w_end : dx;
-    if (T == 1 && half_last) w = dx * 0.25f;
-    s += (double)(w * y);
-  }
-  // exclusive warp scan of the lane totals
-  double incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  double acc = incl - s;
-  for (int i = lo; i < hi; ++i) {
-    float v = vs[i];
-    if (mode == 2) v = expf(v);
-    const float y = mode ? v * v : v;
-    float w = (i == 0 || (half_last && i == T - 1)) ? w_end : dx;
-    if (T == 1 && half_last) w = dx * 0.25f;
-    acc += (double)(w * y);
-    out[i] = (float)acc;
-  }
+  cumtrapz_warp(x + (x_batched ? (size_t)warp * T : 0), vol + (size_t)warp * T, T, mode, half_last, V + (size_t)warp * T, lane);
 }
 
 // ------------------------------------------------------------------------------------------ vol_cov

@@ -28,7 +28,48 @@ struct MllParams {
   float jitter; int max_tries;
   float* scratch;                       // gridDim.x * Tp * Tp
   float* dinv;                          // gridDim.x * nb * 64 * 64
+  // tensor-core batched kernel only: prefix built in-kernel from the raw volatility path (V == nullptr), and series
+  // b >= ready_from wait until *ready != 0 (their inputs are still in flight on a copy stream; volt_mll_grad_vol_host)
+  const float* vol_in; const float* x_in; int x_batched, vol_mode;
+  const int* ready; int ready_from;
 };
+
+// CumTrapz of one series by one warp (VolKernel.py:4-10).  torch.cumsum on CPU accumulates float32 data in a double
+// accumulator and rounds each prefix to float32; same here (per-lane sequential double sums + a warp scan of the lane
+// totals), so the result equals the reference's to the last bit except for double-rounding ties.  `out` may be shared
+// or global memory.
+__device__ __forceinline__ void cumtrapz_warp(const float* __restrict__ xs, const float* __restrict__ vs, int T, int mode, int half_last,
+                                              float* out, int lane) {
+  const float dx = xs[1] - xs[0];
+  const float w_end = dx * 0.5f;
+  const int seg = (T + 31) / 32;
+  const int lo = min(lane * seg, T), hi = min(lo + seg, T);
+  double s = 0.0;
+  for (int i = lo; i < hi; ++i) {
+    float v = vs[i];
+    if (mode == 2) v = expf(v);
+    const float y = mode ? v * v : v;
+    float w = (i == 0 || (half_last && i == T - 1)) ? w_end : dx;
+    if (T == 1 && half_last) w = dx * 0.25f;
+    s += (double)(w * y);
+  }
+  double incl = s;   // exclusive warp scan of the lane totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  double acc = incl - s;
+  for (int i = lo; i < hi; ++i) {
+    float v = vs[i];
+    if (mode == 2) v = expf(v);
+    const float y = mode ? v * v : v;
+    float w = (i == 0 || (half_last && i == T - 1)) ? w_end : dx;
+    if (T == 1 && half_last) w = dx * 0.25f;
+    acc += (double)(w * y);
+    out[i] = (float)acc;
+  }
+}
 
 struct RolloutParams {
   int B, n, S, H, k, mean_kind, joint;   // joint = 1: one-shot multi-point draw (no feedback of samples)
