@@ -316,14 +316,15 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   // waiting CTAs hold.  The prefix sums (CumTrapz) are built inside the kernel: no second launch, no second tail.
   static cudaStream_t s_copy = nullptr, s_comp = nullptr;
   static cudaEvent_t ev0 = nullptr;
-  static int* h_flags = nullptr;   // pinned {0, 1}
+  static int* h_flags = nullptr;   // pinned {0, 0 | 1 | timeout read-back}
   if (!s_copy) {
     VOLT_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
     VOLT_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     VOLT_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
-    VOLT_CUDA(cudaHostAlloc(&h_flags, 2 * sizeof(int), cudaHostAllocDefault));
+    VOLT_CUDA(cudaHostAlloc(&h_flags, 4 * sizeof(int), cudaHostAllocDefault));
     h_flags[0] = 0;
-    h_flags[1] = 1;
+    h_flags[1] = 0;
+    h_flags[2] = 1;
   }
   void* vflag = nullptr;
   s = get_workspace(128, &vflag, 12);
@@ -343,7 +344,7 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   const bool gated = batched_tc && (T % 32 == 0) && B >= 2 * slots;
   const int B0 = gated ? slots : B;
   const size_t n0 = (size_t)B0 * T;
-  VOLT_CUDA(cudaMemcpyAsync(d_flag, h_flags, sizeof(int), cudaMemcpyHostToDevice, s_copy));
+  VOLT_CUDA(cudaMemcpyAsync(d_flag, h_flags, 2 * sizeof(int), cudaMemcpyHostToDevice, s_copy));   // arrival flag, timeout flag
   VOLT_CUDA(cudaMemcpyAsync(d_x, x, (size_t)T * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_noise, noise, n_noise * 4, cudaMemcpyHostToDevice, s_copy));
   VOLT_CUDA(cudaMemcpyAsync(d_vol, vol, n0 * 4, cudaMemcpyHostToDevice, s_copy));
@@ -359,6 +360,9 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
     p.vol_mode = VOLT_VOL_SIGMA;
     p.ready = gated ? d_flag : nullptr;
     p.ready_from = B0;
+    p.ready_timeout = d_flag + 1;
+    // ~0.6 us per poll (measured): 20 ms plus the time the remaining bytes would need at 1 GB/s
+    p.ready_spins = 32768 + (long long)((bt - n0) * 8 / 600);
     s = launch_mll_batched_tc(p, s_comp);
   } else {
     s = volt_mll_grad_vol(d_x, 0, d_vol, VOLT_VOL_SIGMA, d_res, d_noise, noise_stride, B, T, jitter, max_tries, d_scal,
@@ -368,19 +372,34 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   if (gated) {   // submitted after the launch: the kernel does not wait for the host to queue these
     const cudaError_t e1 = cudaMemcpyAsync(d_vol + n0, vol + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy);
     const cudaError_t e2 = cudaMemcpyAsync(d_res + n0, resid + n0, (bt - n0) * 4, cudaMemcpyHostToDevice, s_copy);
-    // the flag must be raised whatever happened above: CTAs are waiting for it (they also give up after ~2 s and trap)
-    cudaError_t e3 = cudaMemcpyAsync(d_flag, h_flags + 1, sizeof(int), cudaMemcpyHostToDevice, s_copy);
-    if (e3 != cudaSuccess) e3 = cudaMemcpy(d_flag, h_flags + 1, sizeof(int), cudaMemcpyHostToDevice);
+    // the flag must be raised whatever happened above: CTAs are waiting for it (they also give up after a while)
+    cudaError_t e3 = cudaMemcpyAsync(d_flag, h_flags + 2, sizeof(int), cudaMemcpyHostToDevice, s_copy);
+    if (e3 != cudaSuccess) e3 = cudaMemcpy(d_flag, h_flags + 2, sizeof(int), cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
       cudaStreamSynchronize(s_comp);
       return check_cuda(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "volt_mll_grad_vol_host: copy of the later series");
     }
   }
   cudaStream_t st = s_comp;
-  VOLT_CUDA(cudaMemcpyAsync(scalars, d_scal, (size_t)B * VOLT_NSCALARS * 4, cudaMemcpyDeviceToHost, st));
-  if (alpha) VOLT_CUDA(cudaMemcpyAsync(alpha, d_alpha, bt * 4, cudaMemcpyDeviceToHost, st));
-  if (info) VOLT_CUDA(cudaMemcpyAsync(info, d_info, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  VOLT_CUDA(cudaStreamSynchronize(st));
+  h_flags[3] = 0;
+  if (gated) VOLT_CUDA(cudaMemcpyAsync(h_flags + 3, d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  for (int pass = 0; pass < 2; ++pass) {
+    VOLT_CUDA(cudaMemcpyAsync(scalars, d_scal, (size_t)B * VOLT_NSCALARS * 4, cudaMemcpyDeviceToHost, st));
+    if (alpha) VOLT_CUDA(cudaMemcpyAsync(alpha, d_alpha, bt * 4, cudaMemcpyDeviceToHost, st));
+    if (info) VOLT_CUDA(cudaMemcpyAsync(info, d_info, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    VOLT_CUDA(cudaStreamSynchronize(st));
+    if (pass == 1 || !gated || h_flags[3] == 0) break;
+    // A CTA gave up waiting for the arrival flag (streams serialised by a profiler or CUDA_LAUNCH_BLOCKING).  Every input
+    // has landed once the copy stream is idle: run the batch again without the gate.
+    VOLT_CUDA(cudaStreamSynchronize(s_copy));
+    MllParams p = base_params(B, T, d_res, d_noise, noise_stride, jitter, max_tries, d_scal, alpha ? d_alpha : nullptr, d_info);
+    p.kind = KIND_VOL;
+    p.vol_in = d_vol;
+    p.x_in = d_x;
+    p.vol_mode = VOLT_VOL_SIGMA;
+    s = launch_mll_batched_tc(p, st);
+    if (s) return s;
+  }
   return VOLT_OK;
 }
 

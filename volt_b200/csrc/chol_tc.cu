@@ -94,17 +94,23 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (HOSTIN && p.ready && b >= p.ready_from) {
       // host-buffer entry: this series' inputs were still being copied when the kernel was launched; the copy stream
-      // writes the flag after them (pure DMA, so it cannot wait for an SM that this CTA is holding)
+      // writes the flag after them (pure DMA, so it cannot wait for an SM that this CTA is holding).  Where streams are
+      // serialised (a profiler replaying this kernel, CUDA_LAUNCH_BLOCKING) the flag cannot arrive while the kernel
+      // runs: after ready_spins polls the CTA reports a timeout and stops, and the host entry re-runs the batch ungated.
       if (tid == 0) {
-        int f;
-        for (long long spins = 0;; ++spins) {
+        int f = 0;
+        for (long long spins = 0; spins < p.ready_spins; ++spins) {
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.ready) : "memory");
           if (f != 0) break;
-          if (spins > (1ll << 23)) __trap();   // ~2 s: the copy stream died; fail the launch instead of hanging the GPU
           __nanosleep(200);
         }
+        if (f == 0) *p.ready_timeout = 1;
+        *c.flag = f;
       }
       __syncthreads();
+      const int arrived = *c.flag;
+      __syncthreads();
+      if (arrived == 0) break;
     }
     if (HOSTIN && p.kind == KIND_VOL && p.vol_in) {
       if (warp == 0)

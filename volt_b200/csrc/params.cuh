@@ -32,6 +32,7 @@ struct MllParams {
   // b >= ready_from wait until *ready != 0 (their inputs are still in flight on a copy stream; volt_mll_grad_vol_host)
   const float* vol_in; const float* x_in; int x_batched, vol_mode;
   const int* ready; int ready_from;
+  int* ready_timeout; long long ready_spins;   // give up after ready_spins polls: *ready_timeout = 1, the CTA stops (the host re-runs)
 };
 
 // CumTrapz of one series by one warp (VolKernel.py:4-10).  torch.cumsum on CPU accumulates float32 data in a double
