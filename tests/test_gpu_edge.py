@@ -157,3 +157,33 @@ def test_host_buffer_entry_equals_device_entry(vb, B, T, pinned):
         assert torch.equal(hs[:, :8], ref["scalars"][:, :8].cpu())
         assert torch.equal(ha, ref["alpha"].cpu())
         assert int(hi.abs().sum()) == 0
+
+
+def test_one_process_two_devices(vb):
+    """Function attributes (opt-in shared memory), helper streams and workspaces are per device: the same process can
+    drive a second GPU (skipped on a one-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B, T = 6, 320
+    x, vol, logy = O.synth_series(B, T, seed=4)
+    resid = logy - logy.mean(-1, keepdim=True)
+    raw = torch.linspace(-2.0, 1.0, B)
+    outs = []
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            dev = torch.device("cuda", d)
+            o = vb.batched.mll_and_grad(x.to(dev), vol.to(dev), resid.to(dev), raw.to(dev), check=True)
+            xl, vl, ll = O.synth_series(1, 2048, seed=6)                      # multi-CTA path: its own streams / attributes
+            ol = vb.batched.mll_and_grad(xl.to(dev), vl.to(dev), (ll - ll.mean()).to(dev), torch.zeros(1, device=dev))
+            pv = vol[:, -1:, None].expand(B, 64, 5).contiguous().to(dev)
+            r, _, _ = vb.ops.rollout(x.to(dev), logy.to(dev), vol.to(dev), pv, eps=torch.ones(B, 64, 5, device=dev), k=5)
+            hs = torch.empty(B, 16).pin_memory()
+            hv, hr, hn = vol.contiguous(), resid.contiguous(), vb.batched.noise_from_raw(raw).contiguous()   # kept alive over the call
+            vb._lib.check(vb._lib.load().volt_mll_grad_vol_host(x.data_ptr(), hv.data_ptr(), hr.data_ptr(), hn.data_ptr(), 1, B, T, 1e-6, 3,
+                                                                hs.data_ptr(), None, None), "volt_mll_grad_vol_host")
+            outs.append((o["mll"].cpu(), ol["mll"].cpu(), r.cpu(), hs[:, 0].clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0][3], outs[0][0])

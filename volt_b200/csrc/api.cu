@@ -68,6 +68,12 @@ int get_workspace(size_t bytes, void** ptr, int slot) {
   return VOLT_OK;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 0;
+  return dev;
+}
+
 int sm_count() {
   static int cached[16] = {0};
   int dev = 0;
@@ -314,9 +320,13 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   // series b, b + grid, ... in order and wait for the flag before touching a series >= B0 (by the time a CTA gets
   // there the data has long arrived).  The flag is written by the copy engine, so it cannot depend on an SM the
   // waiting CTAs hold.  The prefix sums (CumTrapz) are built inside the kernel: no second launch, no second tail.
-  static cudaStream_t s_copy = nullptr, s_comp = nullptr;
-  static cudaEvent_t ev0 = nullptr;
-  static int* h_flags = nullptr;   // pinned {0, 0 | 1 | timeout read-back}
+  struct HostCtx { cudaStream_t s_copy, s_comp; cudaEvent_t ev0; int* h_flags; };   // per device
+  static HostCtx g_ctx[16] = {};
+  HostCtx& hc = g_ctx[device_slot()];
+  cudaStream_t& s_copy = hc.s_copy;
+  cudaStream_t& s_comp = hc.s_comp;
+  cudaEvent_t& ev0 = hc.ev0;
+  int*& h_flags = hc.h_flags;      // pinned {0, 0 | 1 | timeout read-back}
   if (!s_copy) {
     VOLT_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
     VOLT_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));

@@ -292,13 +292,12 @@ int launch_mll_batched_simt(MllParams p, cudaStream_t st) {
     set_error("mll_batched: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);
     return VOLT_ERR_ARG;
   }
-  static bool attr_done = false;
-  static size_t attr_smem = 0;
-  if (!attr_done || smem > attr_smem) {
+  static size_t attr_smem_dev[16] = {};   // function attributes are per device
+  size_t& attr_smem = attr_smem_dev[device_slot()];
+  if (smem > attr_smem) {
     int s = check_cuda(cudaFuncSetAttribute(mll_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(mll_batched_kernel)");
     if (s) return s;
-    attr_done = true;
     attr_smem = smem;
   }
   int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -393,7 +393,8 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   if (mp.diag_add) VOLT_CUDA(cudaMemcpyAsync(&dadd0, mp.diag_add + (size_t)b * mp.diag_stride, 4, cudaMemcpyDeviceToHost, st));
   if (mp.kind == KIND_BM || mp.diag_add) VOLT_CUDA(cudaStreamSynchronize(st));
   p.scale = scale;
-  static bool attr = false;
+  static bool attr_dev[16] = {};   // function attributes, streams and events are per device
+  bool& attr = attr_dev[device_slot()];
   if (!attr) {
     VOLT_CUDA(cudaFuncSetAttribute(large_diagpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     VOLT_CUDA(cudaFuncSetAttribute(large_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
@@ -404,8 +405,13 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   // P+1, on the critical path (stream `st`), and (b) everything to the right of them, which only has to be finished
   // before the next deferred update touches the same tiles -- it runs on a second stream while panel P+1 (a chain of
   // 1-CTA diagonal kernels, TRSM panels and narrow updates that idles most of the GPU) is being factored.
-  static cudaStream_t sb = nullptr;
-  static cudaEvent_t ev_panel = nullptr, ev_rest = nullptr, ev_join = nullptr;
+  struct LookAhead { cudaStream_t sb; cudaEvent_t ev_panel, ev_rest, ev_join; };
+  static LookAhead la_dev[16] = {};
+  LookAhead& la = la_dev[device_slot()];
+  cudaStream_t& sb = la.sb;
+  cudaEvent_t& ev_panel = la.ev_panel;
+  cudaEvent_t& ev_rest = la.ev_rest;
+  cudaEvent_t& ev_join = la.ev_join;
   if (!sb) {
     VOLT_CUDA(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
     VOLT_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));

@@ -34,8 +34,35 @@ namespace tc {
 // HOSTIN = true: the instance behind volt_mll_grad_vol_host -- prefix sums built in-kernel from the raw volatility path and
 // an arrival flag for series whose inputs are still being copied (params.cuh); kept out of the device-pointer instance,
 // whose register allocation it would disturb (measured: +2 % on the c2 kernel time when compiled in unconditionally).
-static __device__ __noinline__ void cumtrapz_to_smem(const float* xs, const float* vs, int T, int mode, float* out, int lane) {
-  cumtrapz_warp(xs, vs, T, mode, 1, out, lane);
+// Whole per-series prologue of that instance as ONE out-of-line call (arrival gate, then the prefix sums into shared
+// memory): the main kernel body only sees a call at a point where nothing but kernel-lifetime values are live.
+// Returns false when the inputs never arrived (the CTA stops, the host re-runs the batch ungated).
+static __device__ __noinline__ bool hostin_prologue(const int* ready, int* ready_timeout, long long ready_spins, const float* xs,
+                                                    const float* vs, int T, int Tp, int mode, float* Vs, int* sflag) {
+  const int tid = threadIdx.x;
+  if (ready) {
+    // This series' inputs were still being copied when the kernel was launched; the copy stream writes the flag after
+    // them (pure DMA, so it cannot wait for an SM that this CTA is holding).  Where streams are serialised (a profiler
+    // replaying this kernel, CUDA_LAUNCH_BLOCKING) the flag cannot arrive while the kernel runs: after ready_spins
+    // polls the CTA reports a timeout and stops.
+    if (tid == 0) {
+      int f = 0;
+      for (long long spins = 0; spins < ready_spins; ++spins) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(ready) : "memory");
+        if (f != 0) break;
+        __nanosleep(200);
+      }
+      if (f == 0) *ready_timeout = 1;
+      *sflag = f;
+    }
+    __syncthreads();
+    const int arrived = *sflag;
+    __syncthreads();
+    if (arrived == 0) return false;
+  }
+  if (tid < 32) cumtrapz_warp(xs, vs, T, mode, 1, Vs, tid);
+  for (int i = T + tid; i < Tp; i += NT) Vs[i] = 0.f;
+  return true;
 }
 
 template <bool TRI, bool HOSTIN = false>
@@ -92,30 +119,10 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   long long tlast = clock64();
 #endif
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    if (HOSTIN && p.ready && b >= p.ready_from) {
-      // host-buffer entry: this series' inputs were still being copied when the kernel was launched; the copy stream
-      // writes the flag after them (pure DMA, so it cannot wait for an SM that this CTA is holding).  Where streams are
-      // serialised (a profiler replaying this kernel, CUDA_LAUNCH_BLOCKING) the flag cannot arrive while the kernel
-      // runs: after ready_spins polls the CTA reports a timeout and stops, and the host entry re-runs the batch ungated.
-      if (tid == 0) {
-        int f = 0;
-        for (long long spins = 0; spins < p.ready_spins; ++spins) {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.ready) : "memory");
-          if (f != 0) break;
-          __nanosleep(200);
-        }
-        if (f == 0) *p.ready_timeout = 1;
-        *c.flag = f;
-      }
-      __syncthreads();
-      const int arrived = *c.flag;
-      __syncthreads();
-      if (arrived == 0) break;
-    }
-    if (HOSTIN && p.kind == KIND_VOL && p.vol_in) {
-      if (warp == 0)
-        cumtrapz_to_smem(p.x_in + (p.x_batched ? (size_t)b * T : 0), p.vol_in + (size_t)b * T, T, p.vol_mode, c.Vs, lane);
-      for (int i = T + tid; i < Tp; i += NT) c.Vs[i] = 0.f;
+    if (HOSTIN) {
+      if (!hostin_prologue((p.ready && b >= p.ready_from) ? p.ready : nullptr, p.ready_timeout, p.ready_spins,
+                           p.x_in + (p.x_batched ? (size_t)b * T : 0), p.vol_in + (size_t)b * T, T, Tp, p.vol_mode, c.Vs, c.flag))
+        break;
     } else {
       for (int i = tid; i < Tp; i += NT) {
         float v = 0.f;
@@ -406,7 +413,8 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
 
 template <bool TRI, bool HOSTIN>
 static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[16] = {};   // function attributes are per device
+  size_t& attr_smem = attr_smem_dev[device_slot()];
   if (smem > attr_smem) {
     int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel<TRI, HOSTIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(mll_batched_tc_kernel)");

@@ -28,6 +28,7 @@ int check_cuda(cudaError_t e, const char* what);
 // Per-device cached workspace (grown on demand, never shrunk).
 int get_workspace(size_t bytes, void** ptr, int slot = 0);
 int sm_count();
+int device_slot();   // current CUDA device clamped to [0, 16): index of the per-device caches (function attributes, streams)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

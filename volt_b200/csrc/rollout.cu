@@ -345,7 +345,8 @@ int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kin
     set_error("ma_paths: T=%d, k=%d exceeds the shared-memory staged path", T, k);
     return VOLT_ERR_ARG;
   }
-  static size_t attr = 0;
+  static size_t attr_dev[16] = {};   // function attributes are per device
+  size_t& attr = attr_dev[device_slot()];
   if (smem > 48 * 1024 && smem > attr) {
     int s = check_cuda(cudaFuncSetAttribute(ma_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(ma_paths_kernel)");
@@ -369,7 +370,8 @@ int launch_rollout(RolloutParams p, cudaStream_t st) {
     set_error("rollout: H=%d, k=%d exceeds shared memory", p.H, p.k);
     return VOLT_ERR_ARG;
   }
-  static size_t attr = 0;
+  static size_t attr_dev[16] = {};   // function attributes are per device
+  size_t& attr = attr_dev[device_slot()];
   if (smem > 48 * 1024 && smem > attr) {
     int s = check_cuda(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(rollout_kernel)");
