@@ -11,7 +11,12 @@
  *     function name ends in `_host`, in which case they are HOST pointers and the call performs the
  *     host<->device copies itself and synchronises before returning.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer entry points only
- *     enqueue work; they never synchronise.
+ *     enqueue work.  They synchronise in two cases only: when a library-owned scratch buffer has to grow (first call at a
+ *     larger size), and on the multi-CTA path for a few very long series (T >= 1536 and B <= 16), which reads one
+ *     4-byte failure flag back per factorisation attempt.
+ *   - scratch memory is owned by the library: one set of buffers per device, grown on demand and reused by every call.
+ *     Calls on one device must therefore be issued in stream order by one host thread at a time; two calls in flight
+ *     on different streams of the same device would share the scratch.  Different devices are independent.
  *   - row-major, contiguous, float32 (the reference's precision).  Batched arrays put the series index first.
  *   - return value: 0 on success, <0 on error (VOLT_ERR_*); volt_last_error() returns the message.
  *     Numerical failure (matrix not positive definite) is NOT an error return: it is reported per matrix in `info`
