@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   const float e_first = ma ? p.e_train[(size_t)b * (n + 1)] : 0.f;
   const float ee_first = need_ee ? p.ee_train[(size_t)b * (n + 1)] : 0.f;
   if (ma && !p.joint) {
-    for (int idx = tid; idx < H; idx += TS) {
+    for (int idx = tid; idx < 1; idx += TS) {   // only step 0 starts from the training-tail sums (see the recurrence below)
       const int m = n + idx;
       const int tc = min(k, max(0, k - idx));        // window terms with absolute index < n      (training y)
       float acc = 0.f;
@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
       float F2 = 0.f, FW = 0.f, FQ = 0.f, QW = 0.f, QQ = 0.f;
       float r_prev = 0.f;          // residual y - mean of the most recently appended point
       float zq[4] = {0.f, 0.f, 0.f, 0.f};   // in-kernel normals: one Philox block per four steps
+      float e_run = 0.f, ee_run = 0.f, eee_run = 0.f;   // running window sums of the moving-average paths
+      const float rho = 1.f - 2.f / (float)(k + 1), w_first = ma ? sw[0] : 0.f, w_last = ma ? sw[k - 1] : 0.f;
       for (int idx = 0; idx < H; ++idx) {
         const int m = n + idx;     // number of conditioning points at this step
         const float pvi = pv[idx];
@@ -244,8 +246,14 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
         // ---- test mean = last element of the MA path over the grown series (EWMA.py:48-50 and twins)
         float m_test;
         if (ma) {
-          float e_m = Pm[idx];   // window y[m-k .. m-1]: training part above, then the draw's own samples out[idx-k+t]
-          for (int t = max(0, k - idx); t < k; ++t) e_m = fmaf(sw[t], out[idx - k + t], e_m);
+          // window y[m-k .. m-1].  Step 0 is the full training-tail sum (Pm[0]); afterwards the window slides by one:
+          // the weights are geometric (w[t-1] = rho w[t], rho = 1 - 2/(k+1)), so
+          //   e[m] = rho (e[m-1] - w[0] y[m-1-k]) + w[k-1] y[m-1]
+          // -- three operations per step instead of a k-term sum (the same filter; rounding differs at the 1e-7 level)
+          float e_m;
+          if (idx == 0) e_m = Pm[0];
+          else e_m = fmaf(rho, e_run - w_first * grown_at(m - 1 - k, n, ytail, tly, y_first, out), w_last * out[idx - 1]);
+          e_run = e_m;
           m_test = e_m;
           if (p.mean_kind == MA_MEANREVERT) {
             if (m >= 1) {
@@ -253,13 +261,19 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
               m_test = e_m - p.mr_theta * (e_prev - mr_lat);
             }
           } else if (need_ee) {
-            float ee_m = Pe[idx];  // window e[m-k .. m-1]; generated part eh[idx-k+t-1]
-            for (int t = max(0, k - idx + 1); t < k; ++t) ee_m = fmaf(sw[t], eh[idx - k + t - 1], ee_m);
+            float ee_m;            // window e[m-k .. m-1] of the e path (training tail, then eh[a] = e[n+1+a]); same recurrence
+            if (idx == 0) ee_m = Pe[0];
+            else ee_m = fmaf(rho, ee_run - w_first * grown_at(m - 1 - k, n + 1, etail, tl, e_first, eh),
+                             w_last * grown_at(m - 1, n + 1, etail, tl, e_first, eh));
+            ee_run = ee_m;
             if (p.mean_kind == MA_DEWMA) {
               m_test = 2.f * e_m - ee_m;
             } else {
-              float eee_m = Pee[idx];  // window ee[m-k .. m-1]; generated part eeh[idx-k+t-1]
-              for (int t = max(0, k - idx + 1); t < k; ++t) eee_m = fmaf(sw[t], eeh[idx - k + t - 1], eee_m);
+              float eee_m;         // window ee[m-k .. m-1] of the ee path (eeh[a] = ee[n+1+a])
+              if (idx == 0) eee_m = Pee[0];
+              else eee_m = fmaf(rho, eee_run - w_first * grown_at(m - 1 - k, n + 1, eetail, tl, ee_first, eeh),
+                                w_last * grown_at(m - 1, n + 1, eetail, tl, ee_first, eeh));
+              eee_run = eee_m;
               m_test = 3.f * e_m - 3.f * ee_m + eee_m;
             }
             if (idx >= 1) eeh[idx - 1] = ee_m;  // ee[n+idx]
