@@ -320,7 +320,8 @@ def test_rollouts_api_shapes_and_side_effects(vb, golden):
     assert abs(float(out[:, 0].mean()) - float(e[-1] + logy[-1] - e[-2])) < 0.1
 
 
-@pytest.mark.parametrize("n,S,H,k", [(64, 33, 7, 5), (256, 64, 30, 25), (100, 130, 12, 100)])
+@pytest.mark.parametrize("n,S,H,k", [(64, 33, 7, 5), (256, 64, 30, 25), (100, 130, 12, 100), (40, 16, 40, 3), (8, 8, 20, 12),
+                                     (30, 9, 6, 1), (26, 12, 31, 25)])
 @pytest.mark.parametrize("mean_func", ["ewma", "dewma", "tewma"])
 def test_rollout_vs_oracle(vb, n, S, H, k, mean_func):
     x, vol, logy = O.synth_series(2, n, seed=31)
