@@ -450,12 +450,19 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.nb = p.Tp / NB;
   const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12);
   const size_t smem_total = 233472, smem_cta_reserved = 1024;   // sm_100: 228 KB per SM, 1 KB reserved per resident CTA
-  // three resident CTAs per SM when the small shared-memory map fits three times (T <= 832); VOLT_TC_CTAS=2 forces the
-  // double-buffered two-CTA kernel (A/B timing)
-  static const int force2 = [] { const char* e = getenv("VOLT_TC_CTAS"); return (e && e[0] == '2') ? 1 : 0; }();
+  // three resident CTAs per SM when the small shared-memory map fits three times (T <= 832); VOLT_TC_CTAS=2 / 3 forces the
+  // double-buffered two-CTA / the three-CTA kernel (A/B timing)
+  static const int forced = [] { const char* e = getenv("VOLT_TC_CTAS"); return e ? atoi(e) : 0; }();   // 2 / 3: A/B timing
+  const int force2 = (forced == 2);
   const size_t smem3 = tc::Y_VEC_OFF + vec;
   const bool hostin = (p.vol_in != nullptr);
-  if (!force2 && 3 * (smem3 + smem_cta_reserved) <= smem_total)
+  // The double-buffered two-CTA instance has the shorter dependency chain per series (T = 512: 0.423 vs 0.445 ms for one
+  // wave at one CTA per SM, 0.551 vs 0.583 ms at two); the three-CTA instance wins once a third chain per SM can be
+  // overlapped (0.757 ms for 444 series vs 0.937).  So: batches of at most two series per SM, and batches whose last
+  // wave would be a single straggler per SM (3 < B / SMs <= 4), take the two-CTA instance.
+  const int sms = sm_count();
+  const bool prefer2 = forced != 3 && ((p.B <= 2 * sms) || (p.B > 3 * sms && p.B <= 4 * sms));
+  if (!force2 && !prefer2 && 3 * (smem3 + smem_cta_reserved) <= smem_total)
     return hostin ? launch_tc<true, true>(p, st, smem3, 3) : launch_tc<true, false>(p, st, smem3, 3);
   const size_t smem = tc::VEC_OFF + vec;
   if (smem > 227 * 1024) {
