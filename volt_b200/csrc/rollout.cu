@@ -147,8 +147,12 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   float* t_pv = Pee + Hp;               // TS*Hp
   float* t_out = t_pv + TS * Hp;
   float* nxt = t_out + TS * Hp;
-  float* t_eps = nxt;                   // base normals (absent with in-kernel Philox)
-  if (p.eps) nxt += TS * Hp;
+  // base normals (absent with in-kernel Philox).  Autoregressive mode reads eps[idx] exactly once, right before it writes
+  // sample idx, so the normals are staged in the OUTPUT tile (no tile of their own: 7 instead of 4 resident CTAs per SM
+  // for the EWMA mean); the one-shot draw may re-read them on a jitter retry and keeps a separate tile.
+  const bool eps_tile = p.eps && p.joint;
+  float* t_eps = eps_tile ? nxt : t_out;
+  if (eps_tile) nxt += TS * Hp;
   float* t_e = nxt;                     // e history  (per draw, index a -> e[n+1+a])
   if (need_e) nxt += TS * Hp;
   float* t_ee = nxt;                    // ee history
@@ -170,10 +174,16 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   // coalesced tile loads
   const size_t base = ((size_t)b * p.S + s0) * H;
   const int ns = min(TS, p.S - s0);
-  for (int idx = tid; idx < ns * H; idx += TS) {
-    const int s = idx / H, h = idx - s * H;
-    t_pv[s * Hp + h] = p.pred_vol[base + idx];
-    if (p.eps) t_eps[s * Hp + h] = p.eps[base + idx];
+  // (draw, step) of a flat tile index advance by a fixed (TS / H, TS % H) per iteration: one division per thread, not one per element
+  const int dq = TS / H, dr = TS - dq * H;
+  {
+    int s = tid / H, h = tid - s * H;
+    for (int idx = tid; idx < ns * H; idx += TS) {
+      t_pv[s * Hp + h] = p.pred_vol[base + idx];
+      if (p.eps) t_eps[s * Hp + h] = p.eps[base + idx];
+      s += dq; h += dr;
+      if (h >= H) { h -= H; ++s; }
+    }
   }
   __syncthreads();
 
@@ -345,9 +355,13 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
     if (p.info) p.info[(size_t)b * p.S + s] = flags;
   }
   __syncthreads();
-  for (int idx = tid; idx < ns * H; idx += TS) {
-    const int s = idx / H, h = idx - s * H;
-    p.samples[base + idx] = t_out[s * Hp + h];
+  {
+    int s = tid / H, h = tid - s * H;
+    for (int idx = tid; idx < ns * H; idx += TS) {
+      p.samples[base + idx] = t_out[s * Hp + h];
+      s += dq; h += dr;
+      if (h >= H) { h -= H; ++s; }
+    }
   }
 }
 
@@ -376,7 +390,7 @@ int launch_rollout(RolloutParams p, cudaStream_t st) {
   int TS = 128;
   const bool need_ee = (p.mean_kind == MA_DEWMA || p.mean_kind == MA_TEWMA);
   const bool need_e = need_ee || p.mean_kind == MA_MEANREVERT;
-  const int ntiles = 2 + (p.eps ? 1 : 0) + (need_e ? 1 : 0) + (need_ee ? 1 : 0);
+  const int ntiles = 2 + ((p.eps && p.joint) ? 1 : 0) + (need_e ? 1 : 0) + (need_ee ? 1 : 0);   // as carved in the kernel
   auto smem_for = [&](int ts) { return sizeof(float) * ((size_t)4 * p.k + 2 + 3 * (size_t)p.Hp + (size_t)ntiles * ts * p.Hp); };
   while (TS > 32 && smem_for(TS) > 56 * 1024) TS >>= 1;   // aim for >= 4 resident CTAs per SM
   const size_t smem = smem_for(TS);
