@@ -170,25 +170,16 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
   uint8_t* RAW = c.X;                                   // 16 KB raw A tile, rows of 128 B, 16-byte chunks XOR-swizzled
   float4 ra[4], rb[2];
   auto gload = [&](int k0) {
-#ifdef VOLT_RB_FIRST
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
-      rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
-    }
-#endif
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
       ra[i] = load_a<PHASE_B>(S, ld, a_row0 + r, a_row_end, k0 + chunk * 4, dinv);
     }
-#ifndef VOLT_RB_FIRST
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
       rb[i] = *reinterpret_cast<const float4*>(SB + (size_t)(b_row0 + r) * ld + k0 + chunk * 4);
     }
-#endif
   };
   gload(k_lo);
   for (int kt = 0; kt < nk; ++kt) {
