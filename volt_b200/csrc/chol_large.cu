@@ -330,6 +330,152 @@ __global__ void __launch_bounds__(NT, 3) large_update_kernel(LargeParams p, int 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(T3_COLS) : "memory");
 }
 
+// ---- the same update on 128 x 256 tiles, one CTA per SM.  A 128 x 64 tile re-stages its 128-row A panel for every 64
+// columns and reads 192 KB of operands for 4.2 MFLOP; four times the columns per staged A tile halve the operand
+// traffic and the per-flop staging work.  TMEM: accumulator 256 columns + two A stages (hi | lo, 32 columns each);
+// shared memory: raw A tile 16 KB + two B stages of 256 rows x 32 floats, hi and lo (2 x 64 KB); double-buffered like
+// gemm_tc (the MMAs of k-tile kt overlap the staging of kt + 1).
+constexpr uint32_t U2_B0 = A_TILE, U2_BSTAGE = 2u * 256u * 128u;               // 64 KB per stage: hi 32 KB | lo 32 KB
+constexpr size_t UPDATE2_SMEM = A_TILE + 2 * U2_BSTAGE + 64;
+constexpr uint32_t U2_ACC = 0, U2_A0 = 256;                                      // stage h: hi at 256 + 64 h, lo at 288 + 64 h
+constexpr uint32_t IDESC256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_tf32_ts256(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(IDESC256), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 1) large_update256_kernel(LargeParams p, int mode, int row_lo, int row_end, int col_lo, int col_hi,
+                                                                int k_lo, int k_hi) {
+  const int ld = p.Tp;
+  const int ncol = (col_hi - col_lo + 255) / 256, nrow = (row_end - row_lo + CM - 1) / CM;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((s_u32(smem_raw) & 1023u) != 0u) __trap();
+  Ctx c;
+  c.X = smem_raw;
+  c.bar = reinterpret_cast<uint64_t*>(smem_raw + A_TILE + 2 * U2_BSTAGE);
+  uint32_t* s_tmem_p = reinterpret_cast<uint32_t*>(smem_raw + A_TILE + 2 * U2_BSTAGE + 16);
+  c.phase = 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(s_tmem_p)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(c.bar, 1);
+    mbar_init(c.bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *s_tmem_p;
+  const int row = 32 * (warp & 3) + lane, half_id = warp >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  float* Cm = mode ? p.Ut : p.W;
+  uint8_t* RAW = c.X;
+  const int nk = (k_hi - k_lo) / 32;
+  for (int t = blockIdx.x; t < ncol * nrow; t += gridDim.x) {
+    const int r_base = row_lo + CM * (t / ncol);      // rows of the C tile
+    const int c_base = col_lo + 256 * (t % ncol);     // columns of the C tile
+    if (!mode && c_base > r_base + CM - 1) continue;  // tile entirely above the diagonal
+    float4 ra[4], rb[8];
+    auto gload = [&](int k0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+        ra[i] = load_a<false>(Cm, ld, r_base + r, row_end, k0 + chunk * 4, nullptr);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+        rb[i] = (c_base + r < col_hi) ? *reinterpret_cast<const float4*>(p.W + (size_t)(c_base + r) * ld + k0 + chunk * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    gload(k_lo);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int h = kt & 1;
+      uint8_t* BH = c.X + U2_B0 + h * U2_BSTAGE;
+      uint8_t* BL = BH + U2_BSTAGE / 2;
+      if (kt >= 2) wait_mma2(c, h);   // MMA group kt-2 has consumed TMEM / shared-memory stage h
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + NT * i, r = idx >> 3, chunk = idx & 7;
+        *reinterpret_cast<float4*>(RAW + r * 128 + ((chunk ^ (r & 7)) << 4)) = ra[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + NT * i;
+        st_split(BH, BL, idx >> 3, idx & 7, rb[i]);
+      }
+      if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
+      __syncthreads();
+      {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = 4 * half_id + q;
+          const float4 v = *reinterpret_cast<const float4*>(RAW + row * 128 + ((chunk ^ (row & 7)) << 4));
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            hi[4 * q + j] = __float_as_uint(e[j]);
+            lo[4 * q + j] = __float_as_uint(e[j] - __uint_as_float(hi[4 * q + j] & 0xffffe000u));
+          }
+        }
+        tmem_st16(c.tmem + lane_base + U2_A0 + (uint32_t)(64 * h + 16 * half_id), hi);
+        tmem_st16(c.tmem + lane_base + U2_A0 + 32u + (uint32_t)(64 * h + 16 * half_id), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint64_t dbh = make_desc(s_u32(BH)), dbl = make_desc(s_u32(BL));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adv = (uint64_t)(2 * ks);
+          const uint32_t ah = c.tmem + U2_A0 + 64 * h + 8 * ks, al = ah + 32;
+          umma_tf32_ts256(c.tmem + U2_ACC, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32_ts256(c.tmem + U2_ACC, ah, dbl + adv, 1u);
+          umma_tf32_ts256(c.tmem + U2_ACC, ah, dbh + adv, 1u);
+        }
+        umma_commit(c.bar + h);
+      }
+    }
+    wait_mma2(c, (nk - 1) & 1);
+    if (nk >= 2) wait_mma2(c, (nk - 2) & 1);
+    tc_fence_after();
+    const int gr = r_base + row;
+#pragma unroll 1
+    for (int piece = 0; piece < 4; ++piece) {
+      const int cc = 128 * half_id + 32 * piece;          // column offset inside the tile
+      const int gc = c_base + cc;
+      float s[32];
+      tmem_ld32(c.tmem + lane_base + U2_ACC + (uint32_t)cc, s);
+      const bool live = gc < col_hi && (mode || (gc & ~63) <= r_base + CM - 1);   // same 64-column blocks as the 128 x 64 tiles
+      if (live && gr < row_end) {
+        float4* dst = reinterpret_cast<float4*>(Cm + (size_t)gr * ld + gc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v = dst[q];
+          v.x -= s[4 * q]; v.y -= s[4 * q + 1]; v.z -= s[4 * q + 2]; v.w -= s[4 * q + 3];
+          dst[q] = v;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // every thread has read its accumulator row before the next tile's first MMA overwrites it
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(c.tmem) : "memory");
+}
+
 // ---- scalars
 __global__ void __launch_bounds__(256) large_finish_kernel(LargeParams p, float jit_used, float* scalars, float* alpha_out, int* info) {
   __shared__ float red[32];
@@ -399,6 +545,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     VOLT_CUDA(cudaFuncSetAttribute(large_diagpanel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     VOLT_CUDA(cudaFuncSetAttribute(large_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LARGE_SMEM));
     VOLT_CUDA(cudaFuncSetAttribute(large_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
+    VOLT_CUDA(cudaFuncSetAttribute(large_update256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE2_SMEM));
     attr = true;
   }
   // Look-ahead over two streams.  The deferred K = 256 update of panel P is split by columns: (a) the columns of panel
@@ -422,6 +569,18 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   auto update = [&](cudaStream_t s2, int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
     const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
     if (nrow <= 0 || ncol <= 0) return;
+    static const int wide = [] { const char* e = getenv("VOLT_UPD256"); return e ? atoi(e) : 1; }();   // 0: 128 x 64 tiles (A/B timing)
+    static const int wide_min = [] { const char* e = getenv("VOLT_UPD256_MIN"); return e ? atoi(e) : 1; }();
+    const int ncol2w = (col_hi - col_lo + 255) / 256;
+    const int live = mode ? nrow * ncol2w : (nrow * ncol2w + 1) / 2 + ncol2w;   // mode 0 keeps the tiles touching the lower triangle
+    if (wide && col_hi - col_lo >= 512 && k_hi - k_lo >= 64 && live >= wide_min) {
+      const int ncol2 = ncol2w;
+      // the look-ahead part on the side stream leaves a quarter of the SMs to the step kernels of the critical path
+      static const int cap_pct = [] { const char* e = getenv("VOLT_UPD256_CAP"); return e ? atoi(e) : 75; }();
+      const int cap = (s2 == st) ? sm_count() : max(1, (cap_pct * sm_count()) / 100);
+      large_update256_kernel<<<min(ncol2 * nrow, cap), NT, UPDATE2_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
+      return;
+    }
     const int grid = min(ncol * nrow, 3 * sm_count());
     large_update_kernel<<<grid, NT, UPDATE_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
   };
