@@ -68,6 +68,13 @@ struct Shared {
   float* LiT; float* tmpbuf;
 };
 
+// Programmatic dependent launch of the step kernels (a chain of ~256 short launches on one stream): a step may be
+// scheduled while its predecessor is still running, so that its prologue (shared-memory carve-up, TMEM allocation,
+// mbarrier init) is off the critical path; it touches global memory only after pdl_wait(), i.e. after the predecessor
+// grid has completed and flushed.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // common prologue: carve shared memory like the batched kernel, allocate TMEM, init the mbarrier
 __device__ __forceinline__ void cta_setup(Shared& sh, uint8_t* base, bool need_tmem) {
   Ctx& c = sh.c;
@@ -117,7 +124,9 @@ constexpr size_t LARGE_SMEM = VEC_OFF + sizeof(float) * (NB + 3 * NB + 32 + 12);
 __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, int j, int kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Shared sh;
+  pdl_release();
   cta_setup(sh, smem_raw, true);
+  pdl_wait();
   Ctx& c = sh.c;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
@@ -210,7 +219,9 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
 __global__ void __launch_bounds__(NT, 2) large_panel_kernel(LargeParams p, int j, int mode, int kp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Shared sh;
+  pdl_release();
   cta_setup(sh, smem_raw, true);
+  pdl_wait();
   Ctx& c = sh.c;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, half_id = warp >> 2, c0 = half_id * 32;
@@ -565,6 +576,20 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     VOLT_CUDA(cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming));
     VOLT_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
+  static const int use_pdl = [] { const char* e = getenv("VOLT_PDL"); return e ? atoi(e) : 1; }();   // 0: plain launches (A/B timing)
+  auto launch_step = [&](auto kernel, int grid, auto... args) -> cudaError_t {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = LARGE_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+  };
   constexpr int PB = 4;  // blocks per panel: trailing updates outside the panel are deferred and applied with K = 256
   auto update = [&](cudaStream_t s2, int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
     const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
@@ -616,7 +641,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     for (int j = 0; j < p.nb; ++j) {
       const int R0 = j * NB, panel_end = min(p.Tp, (j / PB + 1) * PB * NB);
       const int rows = p.Tp - (R0 + NB);
-      large_diagpanel_kernel<<<max(1, (rows + CM - 1) / CM), NT, LARGE_SMEM, st>>>(p, j, (j / PB) * PB * NB);
+      VOLT_CUDA(launch_step(large_diagpanel_kernel, max(1, (rows + CM - 1) / CM), p, j, (j / PB) * PB * NB));
       if (rows > 0 && R0 + NB == panel_end) { s = deferred(0, panel_end, rest_pending); if (s) return s; }
     }
     s = join(rest_pending);
@@ -632,7 +657,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     bool rest_pending = false;
     for (int k = 0; k < p.nb; ++k) {
       const int R0 = k * NB, rows_done = R0 + NB, panel_end = min(p.Tp, (k / PB + 1) * PB * NB);
-      large_panel_kernel<<<(rows_done + CM - 1) / CM, NT, LARGE_SMEM, st>>>(p, k, 1, (k / PB) * PB * NB);
+      VOLT_CUDA(launch_step(large_panel_kernel, (rows_done + CM - 1) / CM, p, k, 1, (k / PB) * PB * NB));
       if (rows_done == panel_end && panel_end < p.Tp) { s = deferred(1, panel_end, rest_pending); if (s) return s; }
     }
     s = join(rest_pending);
