@@ -10,7 +10,9 @@ A "step" is one exact MLL + gradient evaluation for every series of the local ba
 series): cumtrapz -> fused build + potrf + forward substitution + trtri (tr A^-1, alpha) -> scalar loss all-reduce.
 `value` is timed with inputs resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks);
 `e2e` is the same metric through the host-buffer C-ABI call (H2D of x / vol / resid / noise and D2H of the per-series
-results inside the timed region).  Other workloads (--workload c1|c3|c4|c5) are for profiling, not bench lines.
+results inside the timed region).  Two secondary objects ride on the c2 line: `rollout` (c4 per-GPU share) and
+`long_series` (c5: one series of T = 8192, tensor-pipe roofline point).  Other workloads (--workload c1|c3) are for
+profiling, not bench lines.
 """
 import argparse
 import json
@@ -125,6 +127,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32, help="series timed on the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true", help="skip the secondary rollout-throughput measurement")
+    ap.add_argument("--no-long", action="store_true", help="skip the secondary long-series (c5) measurement")
     args = ap.parse_args()
 
     import torch
@@ -279,6 +282,31 @@ def main():
     else:
         roll_ms = 0.0
 
+    # secondary: config c5 of BASELINE.json -- ONE series of T = 8192 through the multi-CTA long-series path (the
+    # tensor-pipe roofline point); reported, never allowed to break the headline line
+    long_ms = 0.0
+    if args.workload == "c2" and not args.no_long:
+        try:
+            lT = 8192
+            lx, lvol, llogy = batched.synth_series(1, lT, dt, start=rank)
+            _, lres = ops.ma_mean("ewma", llogy.to(dev), K_EWMA, want_resid=True)
+            lnoise = batched.noise_from_raw(torch.full((1,), RAW_NOISE, device=dev))
+            lxd, lvd = lx.to(dev), lvol.to(dev)
+            for _ in range(2):   # rank-local calls only (no collective inside a try block)
+                lout = ops.mll_grad("vol", lxd, lvd, lres, lnoise, check=False)
+            torch.cuda.synchronize()
+            lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            for a, b in lev:
+                a.record()
+                lout = ops.mll_grad("vol", lxd, lvd, lres, lnoise, check=False)
+                b.record()
+            torch.cuda.synchronize()
+            assert int(lout["info"].abs().sum()) == 0
+            long_ms = sum(a.elapsed_time(b) for a, b in lev) / len(lev)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] long-series measurement skipped: {exc}", file=sys.stderr)
+            long_ms = 0.0
+
     t = torch.tensor([total_ms, e2e_t * 1e3, kern_ms, roll_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -315,6 +343,13 @@ def main():
         gpu_launches=int(launches),
         clocks=clocks,
         rollout=roll,
+        long_series=(dict(metric="MLL+grad evals/sec, one series of T=8192 (config c5, multi-CTA path)", ms_per_eval=long_ms,
+                          value=1e3 / long_ms, unit="evals/s", n_gpus=1,
+                          roofline=dict(bound="tensor", achieved=(2.0 * 8192 ** 3 / 3.0 + 4.0 * 8192 ** 2) / (long_ms * 1e-3) / 1e12,
+                                        peak=peaks()["tf"], unit="TFLOP/s",
+                                        frac=(2.0 * 8192 ** 3 / 3.0 + 4.0 * 8192 ** 2) / (long_ms * 1e-3) / 1e12 / peaks()["tf"],
+                                        note="algorithmic flops (potrf + trtri); 3x are issued (3xTF32); peak = measured bf16 dense GEMM"))
+                     if long_ms > 0 else None),
         roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=traffic,
                       kernel="mll_batched_tc_kernel (+ cumtrapz_kernel, <1% of the time)", ms_per_launch=kern_ms, bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
         roofline_tensor=dict(bound="tensor", achieved=ach_tf, peak=pk["tf"], unit="TFLOP/s", frac=ach_tf / pk["tf"],
