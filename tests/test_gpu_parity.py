@@ -414,10 +414,10 @@ def test_full_size_c3_shape(vb):
     assert relerr(out["draw_noise"][3], ref["draw_noise"]) < 2e-3
 
 
-@pytest.mark.parametrize("T", [2048, 4096, 8192])
+@pytest.mark.parametrize("T", [1600, 2048, 2112, 4096, 8192])
 def test_long_series_c5_shape(vb, T):
-    """BASELINE config 5 shape (one long series, T up to 8192) through the same tcgen05 blocked-Cholesky kernel
-    (one CTA per series at this size: functional, not yet the multi-CTA roofline point -- DESIGN.md section 8)."""
+    """BASELINE config 5 shape (one long series, T up to 8192) through the multi-CTA long-series path (DESIGN.md section
+    3.1b); 1600 and 2112 are not multiples of the 256-column update tiles (partial tiles, ragged last panel)."""
     x, vol, logy = vb.batched.synth_series(1, T)
     _, resid = vb.ops.ma_mean("ewma", logy.cuda(), 25, want_resid=True)
     raw = torch.tensor([1e-5]).cuda()
