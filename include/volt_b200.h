@@ -14,9 +14,11 @@
  *     enqueue work.  They synchronise in two cases only: when a library-owned scratch buffer has to grow (first call at a
  *     larger size), and on the multi-CTA path for a few very long series (T >= 1536 and B <= 16), which reads one
  *     4-byte failure flag back per factorisation attempt.
- *   - scratch memory is owned by the library: one set of buffers per device, grown on demand and reused by every call.
- *     Calls on one device must therefore be issued in stream order by one host thread at a time; two calls in flight
- *     on different streams of the same device would share the scratch.  Different devices are independent.
+ *   - scratch memory is owned by the library: one arena per (device, stream), grown on demand and reused by every call on
+ *     that stream.  Work on one stream is ordered, so calls issued to the same stream never overlap on the scratch; calls
+ *     on different streams of one device, from one or several host threads, use different arenas and may run
+ *     concurrently.  The `_host` entry points run on library-owned streams with their own arenas, so they may be mixed
+ *     freely with device-pointer calls in flight.  volt_release_workspaces() frees every arena of the current device.
  *   - row-major, contiguous, float32 (the reference's precision).  Batched arrays put the series index first.
  *   - return value: 0 on success, <0 on error (VOLT_ERR_*); volt_last_error() returns the message.
  *     Numerical failure (matrix not positive definite) is NOT an error return: it is reported per matrix in `info`
@@ -76,6 +78,9 @@ long long volt_launch_count(void);
  * products (kept for A/B measurement; both are CUDA paths).  Also settable with VOLT_MLL_IMPL=tc|simt.  Returns the
  * previous setting (-1 if never set). */
 int volt_set_mll_impl(int impl);
+/* Free every cached scratch arena of the current device (synchronises the device first).  The reference's counterpart is
+ * torch.cuda.empty_cache() at voltron/rollout_utils.py:49,92; the arenas are re-created on demand by the next call. */
+int volt_release_workspaces(void);
 
 /* CumTrapz(y, x)  -- voltron/kernels/VolKernel.py:4-10.
  * x (T) or (B,T) if x_batched; y (B,T) encoded per `vol_mode`; half_last=1 reproduces the reference weights

@@ -388,7 +388,8 @@ def gpcv_neg_elbo(x, y, var_mean, chol_var, raw_vol, constant, nq=75):
 
 def gpcv_init(x, y):
     """SingleTaskVariationalGP.initialize_variational_parameters with param="exp" (single_task_variational_gp.py:204-253)
-    at the default BMKernel (vol = 0.2).  Returns (variational_mean, chol_variational_covar)."""
+    at the default BMKernel (vol = 0.2).  Returns (variational_mean, chol_variational_covar, constant): the last line of
+    the reference routine (:254) also sets the ConstantMean to log(mean(running_std)), running_std AFTER the [:10] patch."""
     n = y.shape[0]
     running_std = torch.stack([y[:i].std(0) for i in range(n)])
     running_std[:10] = running_std[10]
@@ -403,19 +404,20 @@ def gpcv_init(x, y):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         S_root = torch.tril(psd_safe_cholesky(S)) * 10.0  # root_decomposition(method="cholesky").root.evaluate().tril() * 10
-    return f, S_root
+    return f, S_root, running_std.mean(0).log().reshape(1)
 
 
-def learn_gpcv(train_x, train_y, train_iters=1000, eps=None, return_state=False):
+def learn_gpcv(train_x, train_y, train_iters=1000, eps=None, return_state=False, returns=None):
     """LearnGPCV (train_utils.py:15-67).  eps (n, 10): the base normals of the final `likelihood(predictive)` marginal
-    (Likelihood.marginal draws settings.num_likelihood_samples = 10 function samples: mean + L_S eps)."""
+    (Likelihood.marginal draws settings.num_likelihood_samples = 10 function samples: mean + L_S eps).
+    returns: fit these scaled returns directly instead of deriving them from prices (example.ipynb cells 5-8)."""
     x = train_x.reshape(-1)
-    y = gpcv_scaled_returns(x, train_y)
-    f0, s_root = gpcv_init(x, y)
+    y = gpcv_scaled_returns(x, train_y) if returns is None else returns
+    f0, s_root, c0 = gpcv_init(x, y)
     vm = f0.clone().requires_grad_(True)
     cv = s_root.clone().requires_grad_(True)
     raw_vol = torch.logit(torch.tensor([0.2], dtype=x.dtype)).requires_grad_(True)       # BMKernel(vol=0.2)
-    const = torch.zeros(1, dtype=x.dtype, requires_grad=True)                               # ConstantMean init
+    const = c0.clone().requires_grad_(True)                                                 # ConstantMean, set by the init (:254)
     # model.parameters() order: variational_mean, chol_variational_covar, mean_module.constant, covar_module.raw_vol
     opt = torch.optim.Adam([vm, cv, const, raw_vol], lr=0.01)
     losses = []
@@ -507,6 +509,45 @@ def train_voltmagpie_model(train_x, train_y, vol_path, train_iters=1000, k=25, t
 
     trace = _adam_loop([raw_noise], closure, train_iters, 0.1)
     return dict(raw_noise=raw_noise.detach(), loss=trace)
+
+
+def train_data_model(train_x, train_y, vol_path, init_weights, train_iters=1000):
+    """voltron/train_utils.py:98-144 -- TrainDataModel: VoltronGP (VoltronGP.py:12-50) with a LogLinearMean
+    (loglinear_mean.py:5-21; bias initialised to mean(price), weights to the randn draw the caller passes), trainable
+    [raw_noise := 1e-5 (RAW, :110), weights, bias] (grad_flags :114), Adam lr 0.1 (:125-127), cached train_cov.
+    train_y are PRICES aligned with train_x."""
+    logy = train_y.log()
+    K = vol_kernel(train_x, vol_path)
+    raw_noise = torch.tensor([1e-5], requires_grad=True)
+    weights = init_weights.clone().reshape(1, 1).requires_grad_(True)
+    bias = logy.exp().mean(-1, keepdim=True).clone().requires_grad_(True)
+
+    def closure():
+        return -exact_mll(K, logy - loglinear_mean(train_x, weights, bias), noise_from_raw(raw_noise))
+
+    trace = _adam_loop([raw_noise, weights, bias], closure, train_iters, 0.1)
+    with torch.no_grad():
+        final = float(closure())
+    return dict(raw_noise=raw_noise.detach(), weights=weights.detach(), bias=bias.detach(), loss=trace, final_loss=final)
+
+
+def model_generate_prediction(train_x, logy, log_vol_path, train_mean, test_mean, test_x, pred_vol, eps):
+    """The class-method GeneratePrediction (voltron/models/VoltronGP.py:62-95, twin VoltMagpie.py:67-99): joint draw at
+    all H test points for ONE predicted vol path, psd_safe_cholesky with its DEFAULT jitter (no 1e-4 here), no
+    likelihood noise, n_sample columns of base normals.  pred_vol (H,), eps (H, n_sample); train_mean (n,), test_mean
+    (H,) are mean_module(train_inputs) / mean_module(test_x).  Returns (H, n_sample) ((H,) for n_sample == 1, the
+    reference's trailing .squeeze(-1))."""
+    full_x = torch.cat((train_x, test_x), dim=-1)
+    full_vol = torch.cat((log_vol_path.exp(), pred_vol), dim=-1)
+    cut = train_x.shape[-1]
+    cov = vol_kernel(full_x, full_vol)
+    K_tr, K_tr_te, K_te = cov[:cut, :cut], cov[:cut, cut:], cov[cut:, cut:]
+    diffs = (logy - train_mean).unsqueeze(-1)
+    L = psd_safe_cholesky(K_tr)
+    pred_mean = K_tr_te.T.matmul(torch.cholesky_solve(diffs, L)) + test_mean.unsqueeze(-1)
+    pred_cov = K_te - K_tr_te.T.matmul(torch.cholesky_solve(K_tr_te, L))
+    samples = psd_safe_cholesky(pred_cov) @ eps
+    return (samples + pred_mean).squeeze(-1)
 
 
 # =============================================================================== synthetic data (SURVEY section 8d)

@@ -32,3 +32,9 @@ def golden():
 @pytest.fixture(scope="session")
 def eval_golden():
     return torch.load(os.path.join(ROOT, "tests", "golden", "eval_golden.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def c1_golden():
+    """BASELINE config c1 (example.ipynb path, n = 256): tests/golden/make_golden_c1.py."""
+    return torch.load(os.path.join(ROOT, "tests", "golden", "c1_golden.pt"), weights_only=False)

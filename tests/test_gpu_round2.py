@@ -1,0 +1,315 @@
+"""GPU parity tests added in round 2 (run on the B200 box: `pytest -m gpu`), all through the C ABI:
+
+* config c1 -- the example.ipynb path (TrainVolModel -> TrainDataModel -> vol_model(test_x).sample() ->
+  dmod.GeneratePrediction) against goldens produced by the reference's own files (tests/golden/make_golden_c1.py);
+* the class-method GeneratePrediction golden (VoltMagpie.py:67-99);
+* config c3 at its full size (256 stations x T = 1024), several series checked;
+* ELEMENT-WISE checks (per-entry relative error with an absolute floor) of alpha and of rollout samples -- the
+  norm-wise `relerr` of test_gpu_parity.py cannot see a wrong small entry;
+* a singular training block on which LAPACK does report failure, compared with the UNPATCHED oracle.
+"""
+import pytest
+import torch
+
+from oracle import volt_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import volt_b200
+
+    volt_b200._lib.require_device()
+    return volt_b200
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64).cpu(), torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def assert_elementwise(got, want, rtol, atol, what=""):
+    """every entry: |got - want| <= rtol |want| + atol."""
+    got, want = torch.as_tensor(got, dtype=torch.float64).cpu(), torch.as_tensor(want, dtype=torch.float64).cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    excess = (got - want).abs() - (rtol * want.abs() + atol)
+    worst = int(excess.argmax())
+    assert float(excess.max()) <= 0.0, (what, "entry", worst, float(got.reshape(-1)[worst]), float(want.reshape(-1)[worst]))
+
+
+class RandnReplay:
+    """torch.randn stand-in that hands back recorded base normals in call order (the goldens record the reference's draws)."""
+
+    def __init__(self, tensors):
+        self.tensors, self.i, self._orig = list(tensors), 0, torch.randn
+
+    def __enter__(self):
+        def rep(*shape, **kw):
+            t = self.tensors[self.i]
+            self.i += 1
+            if len(shape) == 1 and not isinstance(shape[0], int):
+                shape = tuple(shape[0])
+            assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+            return t.clone().to(device=kw.get("device", "cpu"))
+        torch.randn = rep
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn = self._orig
+        return False
+
+
+# ------------------------------------------------------------------------------------------------ config c1
+def test_c1_example_path_golden(vb, c1_golden):
+    """example.ipynb cells 11-15 at n = 256: every stage against the reference's own run.
+    Reference: voltron/train_utils.py:69-95, 98-144; voltron/models/VoltronGP.py:12-50, 62-95; BMGP.py:9-28."""
+    d = c1_golden["data"]
+    train_x, px, vol, test_x = d["train_x"], d["px"], d["vol"], d["test_x"]
+    gv = c1_golden["train_vol"]
+    torch.manual_seed(2019)
+    vmod, vlh = vb.TrainVolModel(train_x, vol, train_iters=gv["iters"])
+    torch.testing.assert_close(vlh.raw_noise.detach(), gv["raw_noise"], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(vmod.covar_module.raw_vol.detach(), gv["raw_vol"], rtol=1e-3, atol=1e-4)
+
+    gd = c1_golden["train_data"]
+    torch.manual_seed(gd["seed"])
+    dmod0, _ = vb.TrainDataModel(train_x, px, vmod, vlh, vol, train_iters=0)
+    for n, p in dmod0.mean_module.named_parameters():      # same randn consumption order as the reference
+        torch.testing.assert_close(p.detach(), gd["init_mean_params"][n], rtol=1e-6, atol=1e-6)
+    torch.manual_seed(gd["seed"])
+    dmod, dlh = vb.TrainDataModel(train_x, px, vmod, vlh, vol, train_iters=gd["iters"])
+    assert [n for n, _ in dmod.named_parameters()] == gd["param_names"]
+    assert [p.requires_grad for p in dmod.parameters()] == gd["requires_grad"]
+    torch.testing.assert_close(dlh.raw_noise.detach(), gd["raw_noise"], rtol=2e-3, atol=2e-4)
+    for n, p in dmod.mean_module.named_parameters():
+        torch.testing.assert_close(p.detach(), gd["mean_params"][n], rtol=2e-3, atol=2e-4)
+    mll = vb.gp.ExactMarginalLogLikelihood(dlh, dmod)
+    loss = -mll(dmod(train_x), px.log())
+    assert relerr(loss.detach(), gd["final_loss"]) < 1e-3
+
+    # cell 15 with the reference's trained parameters (so that the comparison below is not loosened by 20 Adam steps)
+    with torch.no_grad():
+        dlh.raw_noise.data = gd["raw_noise"].clone()
+        for n, p in dmod.mean_module.named_parameters():
+            p.copy_(gd["mean_params"][n])
+        vlh.raw_noise.data = gv["raw_noise"].clone()
+        vmod.covar_module.raw_vol.data = gv["raw_vol"].clone()
+    dmod.eval()
+    dlh.eval()
+    dmod.vol_model.eval()
+    post = dmod.vol_model(test_x)
+    assert relerr(post.mean, c1_golden["vol_post"]["mean"]) < 1e-3
+    assert relerr(post.covariance_matrix, c1_golden["vol_post"]["cov"]) < 2e-3
+    for p in c1_golden["predict"]:
+        with RandnReplay([p["vol_eps"]]):
+            vol_pred = dmod.vol_model(test_x).sample().exp()
+        assert vol_pred.shape == p["vol_pred"].shape
+        assert_elementwise(vol_pred, p["vol_pred"], 2e-3, 0.0, "vol_pred")
+        with RandnReplay([p["eps"]]):
+            px_pred = dmod.GeneratePrediction(test_x, p["vol_pred"], p["npx"])
+        assert px_pred.shape == p["px_pred"].shape          # (H,) for npx == 1: the reference's trailing squeeze(-1)
+        assert_elementwise(px_pred, p["px_pred"], 1e-3, 0.0, "px_pred")
+
+
+def test_genpred_method_golden(vb, golden):
+    """The class-method GeneratePrediction of VoltMagpie (VoltMagpie.py:67-99) with a ConstantMean, n_sample = 4."""
+    g = golden["genpred_method"]
+    vmod, vlh = vb.TrainVolModel(g["train_x"], g["vol"], train_iters=0)
+    volt, lh = vb.TrainVoltMagpieModel(g["train_x"], g["train_y"][1:], vmod, vlh, g["vol"], train_iters=0, k=10,
+                                       mean_func="constant")
+    with torch.no_grad():
+        for n, p in volt.mean_module.named_parameters():
+            p.copy_(g["mean_params"][n])
+    with RandnReplay([g["eps"]]):
+        out = volt.GeneratePrediction(g["test_x"], g["pred_vol"], n_sample=4)
+    assert out.shape == g["samples"].shape
+    assert_elementwise(out, g["samples"], 1e-3, 0.0, "genpred_method")
+
+
+# ------------------------------------------------------------------------------------------------ config c3, full size
+def test_full_size_c3(vb):
+    """BASELINE config 3 at its full size (256 stations x T = 1024, dt = 1/365, EWMA k = 25): identities on every series,
+    five series against the fp64 oracle (MLL 1e-4, gradient 2e-3, alpha element-wise)."""
+    B, T, k = 256, 1024, 25
+    x, vol, logy = vb.batched.synth_series(B, T, dt=1.0 / 365)
+    _, resid = vb.ops.ma_mean("ewma", logy.cuda(), k, want_resid=True)
+    raw = torch.full((B,), 1e-5).cuda()
+    out = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid, raw, check=True)
+    sc = out["scalars"]
+    assert bool(torch.isfinite(sc).all()) and int(out["info"].abs().sum()) == 0
+    torch.testing.assert_close(sc[:, 1], 0.5 * (sc[:, 5] - sc[:, 4]) / T, rtol=1e-5, atol=1e-7)
+    assert relerr((out["alpha"] * resid).sum(-1), sc[:, 3]) < 1e-3
+    for b in (0, 3, 100, 147, 255):
+        ref = O.volt_mll_and_grad(x.double(), vol[b].double(), resid[b].cpu().double(), raw[b].cpu().double())
+        assert relerr(out["mll"][b], ref["mll"]) < 1e-4
+        assert relerr(out["draw_noise"][b], ref["draw_noise"]) < 2e-3
+        assert_elementwise(out["alpha"][b], ref["alpha"], 2e-3, 1e-4 * float(ref["alpha"].abs().max()), f"alpha[{b}]")
+
+
+# ------------------------------------------------------------------------------------------------ element-wise checks
+@pytest.mark.parametrize("T", [64, 200, 512, 900])
+@pytest.mark.parametrize("raw", [1e-5, -4.0])
+def test_alpha_elementwise_vs_fp64_oracle(vb, T, raw):
+    """alpha = A^-1 r entry by entry (it is dMLL/dmean x T, i.e. the gradient of every mean parameter): per-entry
+    relative 2e-3 with an absolute floor of 1e-4 x max|alpha| (entries that cancel to ~0 carry fp32 rounding of the
+    large ones)."""
+    B, k = 3, 10
+    x, vol, logy = O.synth_series(B, T, seed=500 + T)
+    resid = torch.stack([logy[b] - O.ma_mean_forward("ewma", x, logy[b], k, x) for b in range(B)])
+    rawt = torch.full((B,), raw)
+    out = vb.batched.mll_and_grad(x.cuda(), vol.cuda(), resid.cuda(), rawt.cuda(), check=True)
+    for b in range(B):
+        ref = O.volt_mll_and_grad(x.double(), vol[b].double(), resid[b].double(), rawt[b].double())
+        assert_elementwise(out["alpha"][b], ref["alpha"], 2e-3, 1e-4 * float(ref["alpha"].abs().max()), f"alpha[{b}]")
+
+
+@pytest.mark.parametrize("n,S,H,k", [(64, 33, 7, 5), (256, 64, 30, 25)])
+@pytest.mark.parametrize("mean_func", ["ewma", "tewma"])
+def test_rollout_samples_elementwise(vb, n, S, H, k, mean_func):
+    """Rollout samples entry by entry, and -- the sharper statement -- the forecast INCREMENT over the last training
+    value entry by entry (log prices are ~2.3 while a 30-step move is ~0.1: a norm-wise 1e-3 on the sample hides a 2 %
+    error of the move).  fp64 oracle, explicit base normals."""
+    x, vol, logy = O.synth_series(2, n, seed=77)
+    g = torch.Generator().manual_seed(n + S + 1)
+    px = torch.cat((logy[:, :1], logy), -1).exp()
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    pred_vol = vol[:, -1:, None] * torch.exp(0.2 * torch.randn(2, S, H, generator=g))
+    eps = torch.randn(2, S, H, generator=g)
+    out, dinfo, sinfo = vb.ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind=mean_func, k=k)
+    for b in range(2):
+        want = O.rollouts(x.double(), px[b].double(), vol[b].log().double(), test_x.double(), pred_vol[b].double(),
+                          eps[b].double(), k, mean_kind=mean_func)
+        assert_elementwise(out[b], want, 1e-3, 0.0, "sample")
+        last = float(logy[b, -1])
+        inc, inc_ref = out[b].double().cpu() - last, want - last
+        assert_elementwise(inc, inc_ref, 5e-3, 2e-4, "increment")
+
+
+# ------------------------------------------------------------------------------------------------ LAPACK-reported failure
+def test_rollout_singular_block_lapack_reports_failure_unpatched_oracle(vb):
+    """A zero-volatility segment duplicates rows of K_tr.  On this input the computed pivot of the first duplicated row is
+    exactly zero, so LAPACK (torch.linalg.cholesky_ex behind psd_safe_cholesky) DOES report failure and the reference
+    takes the jitter branch (rollout_utils.py:35, jitter = 1e-4); the GPU predicate fails the same pivot.  Compared with
+    the oracle as is -- no monkey-patching."""
+    n, S, H, k = 48, 7, 4, 10
+    picked = None
+    for seed in range(100, 140):     # the LAPACK outcome on an exactly singular matrix can depend on the host's BLAS path
+        x, vol, logy = O.synth_series(1, n, seed=seed)
+        vol = vol.clone()
+        vol[0, 10:20] = 0.0
+        _, info_t = torch.linalg.cholesky_ex(O.vol_kernel(x, vol[0]))
+        if int(info_t) > 0:
+            picked = (x, vol, logy)
+            break
+    assert picked is not None, "no candidate on which LAPACK reports failure"
+    x, vol, logy = picked
+    g = torch.Generator().manual_seed(5)
+    pred_vol = 0.2 * torch.exp(0.1 * torch.randn(1, S, H, generator=g))
+    eps = torch.randn(1, S, H, generator=g)
+    out, dinfo, sinfo = vb.ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind="ewma", k=k, check=False)
+    assert int(sinfo[0]) == 0 and int((dinfo & 5).sum()) == 0
+    px = torch.cat((logy[:, :1], logy), -1).exp()
+    test_x = x[-1] + x[1] * torch.arange(1, H + 1)
+    lv = vol[0].clamp_min(1e-30).log()      # exp(log(1e-30))^2 underflows to 0 in float32, like the zero vol itself
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.rollouts(x, px[0], lv, test_x, pred_vol[0], eps[0], k)      # float32, like the reference
+    assert relerr(out[0], want) < 1e-3
+    assert_elementwise(out[0], want, 1e-3, 0.0, "singular-block sample")
+
+
+# ------------------------------------------------------------------------------------------------ GPCV pin (real GPyTorch output)
+def test_gpcv_reproduces_notebook_elbo_trace(vb):
+    """example.ipynb cell 8 records the loss trace the REAL GPyTorch printed while fitting the GPCV model to the
+    notebook's seeded data; the device-resident loop (volt_b200.gpcv, closed-form gradients, CUDA-graph replay) must print
+    the same numbers at every recorded iteration (1, 51, ..., 451).  Reference: voltron/train_utils.py:15-67,
+    models/single_task_variational_gp.py:204-254, likelihoods/volatility_likelihood.py:44-52."""
+    from notebook_data import NOTEBOOK_GPCV_TRACE, notebook_series
+
+    full_x, full_y, _, _, _ = notebook_series()
+    _, st = vb.gpcv.learn_gpcv(full_x, None, train_iters=451, return_state=True, returns=full_y.reshape(1, -1))
+    losses = st.losses[:, 0].cpu()
+    for it, want in NOTEBOOK_GPCV_TRACE.items():
+        assert abs(float(losses[it - 1]) - want) < 2e-3, (it, float(losses[it - 1]), want)
+
+
+# ------------------------------------------------------------------------------------------------ ADVICE (round 1) regressions
+def test_fused_adam_loop_long_series_runs_eagerly(vb):
+    """A single series of T >= 1536 takes the multi-CTA path, whose failure-flag read-back cannot be captured in a CUDA
+    graph: the fused loop must run it eagerly (no swallowed capture error, current stream untouched) and still match the
+    oracle's Adam trajectory."""
+    import warnings
+
+    T, iters, k = 1600, 3, 25
+    x, vol, logy = O.synth_series(1, T, seed=12)
+    px = logy[0].exp()
+    vmod, vlh = vb.TrainVolModel(x, vol[0], train_iters=0)
+    before = torch.cuda.current_stream()
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)      # a failed capture would warn
+        volt, lh = vb.TrainVoltMagpieModel(x, px, vmod, vlh, vol[0], train_iters=iters, k=k)
+    assert torch.cuda.current_stream() == before
+    want = O.train_voltmagpie_model(x, px, vol[0], train_iters=iters, k=k)
+    torch.testing.assert_close(lh.raw_noise.detach().cpu(), want["raw_noise"], rtol=1e-3, atol=1e-4)
+
+
+def test_rollout_philox_chunks_draw_distinct_normals(vb):
+    """Batches of more than 65535 series are launched in chunks; the in-kernel Philox counter is keyed on the GLOBAL series
+    index, so series b and b + 65535 (same data) must not share their base normals."""
+    n, S, H, B = 8, 2, 3, 65535 + 3
+    x, vol, logy = O.synth_series(1, n, seed=3)
+    pv = torch.full((B, S, H), 0.2)
+    out, _, _ = vb.ops.rollout(x.cuda(), logy.expand(B, n).contiguous().cuda(), vol.expand(B, n).contiguous().cuda(), pv.cuda(),
+                               eps=None, k=5, seed=9, check=False)
+    assert not torch.equal(out[0], out[65535]) and not torch.equal(out[1], out[65536])
+    again, _, _ = vb.ops.rollout(x.cuda(), logy.expand(B, n).contiguous().cuda(), vol.expand(B, n).contiguous().cuda(), pv.cuda(),
+                                 eps=None, k=5, seed=9, check=False)
+    assert torch.equal(out, again)
+
+
+def test_batched_time_grid_rows_are_validated(vb):
+    x, vol, logy = O.synth_series(3, 40, seed=1)
+    resid = (logy - logy.mean(-1, keepdim=True)).cuda()
+    noise = torch.full((3,), 0.5).cuda()
+    one = vb.ops.mll_grad("vol", x.cuda(), vol.cuda(), resid, noise)
+    row = vb.ops.mll_grad("vol", x.reshape(1, -1).cuda(), vol.cuda(), resid, noise)       # (1, T): broadcast over the batch
+    assert torch.equal(one["scalars"], row["scalars"])
+    with pytest.raises(ValueError):
+        vb.ops.mll_grad("vol", x.reshape(1, -1).repeat(2, 1).cuda(), vol.cuda(), resid, noise)
+
+
+def test_two_streams_and_host_entry_do_not_share_scratch(vb):
+    """Boundary hygiene: scratch arenas are keyed by stream, and the host-buffer entry runs on library-owned streams with
+    arenas of its own -- device-pointer calls in flight on two user streams plus a host-entry call give the same bits as
+    the same calls run one after the other."""
+    B, T = 300, 256
+    x, vol, logy = O.synth_series(B, T, seed=40)
+    resid = logy - logy.mean(-1, keepdim=True)
+    raw = torch.linspace(-3, 1, B)
+    noise = torch.nn.functional.softplus(raw) + 1e-4
+    xd, vd, rd, nd = x.cuda(), vol.cuda(), resid.cuda(), noise.cuda()
+    vd2 = (vol * 1.3).cuda()
+    ref1 = vb.ops.mll_grad("vol", xd, vd, rd, nd)["scalars"].clone()
+    ref2 = vb.ops.mll_grad("vol", xd, vd2, rd, nd)["scalars"].clone()
+    torch.cuda.synchronize()
+    lib = vb._lib.load()
+    hs = torch.empty(B, 16).pin_memory()
+    hi = torch.empty(B, dtype=torch.int32).pin_memory()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            o1 = vb.ops.mll_grad("vol", xd, vd, rd, nd)
+        with torch.cuda.stream(s2):
+            o2 = vb.ops.mll_grad("vol", xd, vd2, rd, nd)
+        vb._lib.check(lib.volt_mll_grad_vol_host(x.data_ptr(), vol.contiguous().data_ptr(), resid.contiguous().data_ptr(),
+                                                 noise.contiguous().data_ptr(), 1, B, T, 1e-6, 3, hs.data_ptr(), None, hi.data_ptr()),
+                      "volt_mll_grad_vol_host")
+        torch.cuda.synchronize()
+        assert torch.equal(o1["scalars"], ref1) and torch.equal(o2["scalars"], ref2)
+        assert torch.equal(hs[:, :7], ref1[:, :7].cpu())
+    assert lib.volt_release_workspaces() == 0
+    again = vb.ops.mll_grad("vol", xd, vd, rd, nd)["scalars"]            # arenas are re-created on demand
+    assert torch.equal(again, ref1)

@@ -103,6 +103,64 @@ def test_golden_genpred_step(golden):
     close(s.reshape(-1), g["samples"].reshape(-1), rtol=1e-5, atol=2e-5)
 
 
+def test_golden_genpred_method(golden):
+    """The class-method GeneratePrediction (VoltMagpie.py:67-99) with a ConstantMean: joint draw, default jitter."""
+    g = golden["genpred_method"]
+    logy = g["train_y"][1:].log()
+    c = g["mean_params"]["constant"].reshape(())
+    n, H = g["train_x"].numel(), g["test_x"].numel()
+    out = O.model_generate_prediction(g["train_x"], logy, g["vol"].log(), c.expand(n), c.expand(H), g["test_x"], g["pred_vol"],
+                                      g["eps"])
+    close(out, g["samples"], rtol=1e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------ config c1: the example.ipynb path
+def test_golden_c1_train_data_model(c1_golden):
+    """TrainDataModel (train_utils.py:98-144) on the notebook's SABR series, n = 256: trained raw_noise / weights / bias
+    and the final loss against the reference's own loop."""
+    d, g = c1_golden["data"], c1_golden["train_data"]
+    out = O.train_data_model(d["train_x"], d["px"], d["vol"], g["init_mean_params"]["weights"], train_iters=g["iters"])
+    close(out["raw_noise"], g["raw_noise"], rtol=1e-4, atol=1e-5)
+    close(out["weights"], g["mean_params"]["weights"], rtol=1e-4, atol=1e-5)
+    close(out["bias"], g["mean_params"]["bias"], rtol=1e-4, atol=1e-5)
+    assert abs(out["final_loss"] - float(g["final_loss"])) < 1e-5 * abs(float(g["final_loss"])) + 1e-6
+
+
+def test_golden_c1_vol_model_and_prediction(c1_golden):
+    """example.ipynb cells 11, 15: TrainVolModel, vol_model(test_x).sample(), dmod.GeneratePrediction(test_x, vol_pred, npx)."""
+    d = c1_golden["data"]
+    tv = O.train_vol_model(d["train_x"], d["vol"], train_iters=c1_golden["train_vol"]["iters"])
+    close(tv["raw_noise"], c1_golden["train_vol"]["raw_noise"], rtol=1e-4, atol=1e-5)
+    close(tv["raw_vol"], c1_golden["train_vol"]["raw_vol"], rtol=1e-4, atol=1e-5)
+    vol = O.bm_vol_from_raw(tv["raw_vol"])
+    mean, cov = O.bmgp_posterior(d["train_x"], d["vol"].log(), d["test_x"], vol, O.noise_from_raw(tv["raw_noise"]))
+    close(mean, c1_golden["vol_post"]["mean"], rtol=1e-4, atol=1e-4)
+    close(cov, c1_golden["vol_post"]["cov"], rtol=1e-3, atol=1e-5)
+    g = c1_golden["train_data"]
+    w, b = g["mean_params"]["weights"], g["mean_params"]["bias"]
+    for p in c1_golden["predict"]:
+        vol_pred = O.mvn_sample(c1_golden["vol_post"]["mean"], c1_golden["vol_post"]["cov"], p["vol_eps"])[0].exp()
+        close(vol_pred, p["vol_pred"], rtol=1e-4, atol=1e-6)
+        out = O.model_generate_prediction(d["train_x"], d["px"].log(), d["vol"].log(), O.loglinear_mean(d["train_x"], w, b),
+                                          O.loglinear_mean(d["test_x"], w, b), d["test_x"], p["vol_pred"], p["eps"])
+        assert out.shape == p["px_pred"].shape
+        close(out, p["px_pred"], rtol=1e-5, atol=2e-5)
+
+
+def test_gpcv_oracle_reproduces_notebook_elbo_trace():
+    """PIN for the GPyTorch variational slice: example.ipynb cell 8 records the loss the real GPyTorch printed while
+    fitting the GPCV model to the notebook's seeded data (cells 2-7).  The oracle, run on the regenerated data, must print
+    the same numbers (first 101 iterations here; the GPU test runs all 451)."""
+    from notebook_data import NOTEBOOK_GPCV_TRACE, notebook_series
+
+    full_x, full_y, _, _, _ = notebook_series()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, st = O.learn_gpcv(full_x, None, train_iters=101, return_state=True, returns=full_y)
+    for it in (1, 51, 101):
+        assert abs(st["losses"][it - 1] - NOTEBOOK_GPCV_TRACE[it]) < 2e-3, (it, st["losses"][it - 1])
+
+
 # ------------------------------------------------------------------ known-answer tests (fp64)
 def _rand_series(T, seed=0, dtype=torch.float64):
     g = torch.Generator().manual_seed(seed)

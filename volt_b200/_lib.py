@@ -23,6 +23,7 @@ _SIGS = {
     "volt_device_check": (c_int, []),
     "volt_launch_count": (c_longlong, []),
     "volt_set_mll_impl": (c_int, [c_int]),
+    "volt_release_workspaces": (c_int, []),
     "volt_cumtrapz": (c_int, [_fp, c_int, _fp, c_int, c_int, c_int, c_int, _fp, c_void_p]),
     "volt_vol_cov": (c_int, [_fp, c_int, _fp, c_int, c_int, c_int, _fp, c_int, _fp, c_void_p]),
     "volt_bm_cov": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_void_p]),

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/volt_b200.h"
 #include "params.cuh"
@@ -30,41 +31,65 @@ int check_cuda(cudaError_t e, const char* what) {
   return VOLT_ERR_CUDA;
 }
 
-// ---- per-device cached workspaces
+// ---- cached workspaces, one arena per (device, slot, stream)
+// Work submitted to one stream is ordered, so kernels that share an arena never overlap; two streams (or the library's own
+// copy / compute streams behind the host-buffer entry) get separate arenas and therefore cannot race on the scratch.
+// Grown on demand (device-wide synchronisation before the old block is freed), released by volt_release_workspaces().
 constexpr int kSlots = 13;
 struct Ws {
+  int slot = 0;
+  cudaStream_t stream = nullptr;
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-static Ws g_ws[16][kSlots];
+static std::vector<Ws> g_ws[16];
 static std::mutex g_mu;
 
-int get_workspace(size_t bytes, void** ptr, int slot) {
+int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || slot < 0 || slot >= kSlots) {
     set_error("get_workspace: bad device/slot");
     return VOLT_ERR_CUDA;
   }
   std::lock_guard<std::mutex> lk(g_mu);
-  Ws& w = g_ws[dev][slot];
+  Ws* w = nullptr;
+  for (Ws& e : g_ws[dev])
+    if (e.slot == slot && e.stream == stream) { w = &e; break; }
+  if (!w) {
+    g_ws[dev].emplace_back();
+    w = &g_ws[dev].back();
+    w->slot = slot;
+    w->stream = stream;
+  }
   if (bytes == 0) bytes = 256;
-  if (w.bytes < bytes) {
-    if (w.ptr) {
+  if (w->bytes < bytes) {
+    if (w->ptr) {
       cudaDeviceSynchronize();
-      cudaFree(w.ptr);
-      w.ptr = nullptr;
-      w.bytes = 0;
+      cudaFree(w->ptr);
+      w->ptr = nullptr;
+      w->bytes = 0;
     }
     const size_t want = (bytes + (size_t)(1 << 20) - 1) / (size_t)(1 << 20) * (size_t)(1 << 20);
-    cudaError_t e = cudaMalloc(&w.ptr, want);
+    cudaError_t e = cudaMalloc(&w->ptr, want);
     if (e != cudaSuccess) {
       set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
-      w.ptr = nullptr;
+      w->ptr = nullptr;
       return VOLT_ERR_ALLOC;
     }
-    w.bytes = want;
+    w->bytes = want;
   }
-  *ptr = w.ptr;
+  *ptr = w->ptr;
+  return VOLT_OK;
+}
+
+static int release_workspaces() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return VOLT_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaDeviceSynchronize();
+  for (Ws& e : g_ws[dev])
+    if (e.ptr) cudaFree(e.ptr);
+  g_ws[dev].clear();
   return VOLT_OK;
 }
 
@@ -177,6 +202,7 @@ const char* volt_last_error(void) { return g_err; }
 int volt_abi_version(void) { return VOLT_ABI_VERSION; }
 int volt_device_check(void) { return device_check(); }
 long long volt_launch_count(void) { return g_launches; }
+int volt_release_workspaces(void) { return release_workspaces(); }
 int volt_set_mll_impl(int impl) {
   const int prev = g_mll_impl;
   g_mll_impl = impl ? 1 : 0;
@@ -197,7 +223,7 @@ int volt_vol_cov(const float* x, int x_batched, const float* vol, int vol_mode, 
   VOLT_REQUIRE(x && vol && K, "volt_vol_cov: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_vol_cov: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
   void* V = nullptr;
-  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1);
+  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1, ST(stream));
   if (s) return s;
   s = launch_cumtrapz(x, x_batched, vol, B, T, vol_mode, 1, (float*)V, ST(stream));
   if (s) return s;
@@ -215,7 +241,7 @@ int volt_ewma(const float* y, int S, int T, int k, float* out, void* stream) {
   VOLT_REQUIRE(y && out, "volt_ewma: null pointer");
   VOLT_REQUIRE(S >= 1 && T >= 1 && k >= 1, "volt_ewma: need S,T,k >= 1 (got %d,%d,%d)", S, T, k);
   void* w = nullptr;
-  int s = get_workspace((size_t)k * sizeof(float), &w, 2);
+  int s = get_workspace((size_t)k * sizeof(float), &w, 2, ST(stream));
   if (s) return s;
   s = launch_ewma_weights(k, (float*)w, ST(stream));
   if (s) return s;
@@ -230,7 +256,7 @@ int volt_ma_mean(const float* y, int S, int T, int k, int kind, float theta, con
   VOLT_REQUIRE(kind >= VOLT_MA_EWMA && kind <= VOLT_MA_MEANREVERT, "volt_ma_mean: bad kind %d", kind);
   VOLT_REQUIRE(kind != VOLT_MA_MEANREVERT || latent, "volt_ma_mean: meanrevert needs latent");
   void* w = nullptr;
-  int s = get_workspace((size_t)k * sizeof(float), &w, 2);
+  int s = get_workspace((size_t)k * sizeof(float), &w, 2, ST(stream));
   if (s) return s;
   s = launch_ewma_weights(k, (float*)w, ST(stream));
   if (s) return s;
@@ -244,7 +270,7 @@ int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_m
   VOLT_REQUIRE(x && vol && resid && scalars, "volt_mll_grad_vol: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
   void* V = nullptr;
-  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1);
+  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1, ST(stream));
   if (s) return s;
   s = launch_cumtrapz(x, x_batched, vol, B, T, vol_mode, 1, (float*)V, ST(stream));
   if (s) return s;
@@ -305,16 +331,6 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
   const size_t n_noise = noise_stride ? (size_t)B : 1;
   // one staging buffer: x | vol | resid | noise | scalars | alpha | info
   const size_t floats = (size_t)T + bt + bt + n_noise + (size_t)B * VOLT_NSCALARS + bt + (size_t)B;
-  void* ws = nullptr;
-  int s = get_workspace(floats * sizeof(float), &ws, 3);
-  if (s) return s;
-  float* d_x = (float*)ws;
-  float* d_vol = d_x + T;
-  float* d_res = d_vol + bt;
-  float* d_noise = d_res + bt;
-  float* d_scal = d_noise + n_noise;
-  float* d_alpha = d_scal + (size_t)B * VOLT_NSCALARS;
-  int* d_info = (int*)(d_alpha + bt);
   // Pipeline: the inputs of the first `B0` series are copied and ONE kernel is launched for the whole batch; the copy of
   // the remaining series runs on the copy stream underneath it, followed by a 4-byte flag.  The persistent CTAs take
   // series b, b + grid, ... in order and wait for the flag before touching a series >= B0 (by the time a CTA gets
@@ -336,8 +352,20 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
     h_flags[1] = 0;
     h_flags[2] = 1;
   }
+  // every arena of this entry (staging, factor scratch, prefix sums) is keyed by the library's own compute stream, so the
+  // call cannot race with work the caller has in flight on their streams through the device-pointer entry points
+  void* ws = nullptr;
+  int s = get_workspace(floats * sizeof(float), &ws, 3, s_comp);
+  if (s) return s;
+  float* d_x = (float*)ws;
+  float* d_vol = d_x + T;
+  float* d_res = d_vol + bt;
+  float* d_noise = d_res + bt;
+  float* d_scal = d_noise + n_noise;
+  float* d_alpha = d_scal + (size_t)B * VOLT_NSCALARS;
+  int* d_info = (int*)(d_alpha + bt);
   void* vflag = nullptr;
-  s = get_workspace(128, &vflag, 12);
+  s = get_workspace(128, &vflag, 12, s_comp);
   if (s) return s;
   int* d_flag = (int*)vflag;
   if (g_mll_impl < 0) {
@@ -419,7 +447,7 @@ int volt_potrf(const float* A, long long a_bstride, int lda, const float* add_di
   VOLT_REQUIRE(A && L, "volt_potrf: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 1 && lda >= T && ldl >= T, "volt_potrf: bad shape");
   void* sc = nullptr;
-  int s = get_workspace((size_t)B * VOLT_NSCALARS * sizeof(float), &sc, 4);
+  int s = get_workspace((size_t)B * VOLT_NSCALARS * sizeof(float), &sc, 4, ST(stream));
   if (s) return s;
   MllParams p = base_params(B, T, nullptr, add_diag, add_stride, jitter, max_tries, (float*)sc, nullptr, info);
   p.kind = KIND_DENSE;
@@ -450,14 +478,14 @@ int volt_bmgp_posterior(const float* x, const float* y, int B, int T, const floa
   VOLT_REQUIRE(B >= 1 && T >= 1 && H >= 1, "volt_bmgp_posterior: bad shape");
   const size_t wfl = (size_t)B * T * (H + 1) + (size_t)B * H * H + (size_t)B * H + (size_t)B * VOLT_NSCALARS;
   void* ws = nullptr;
-  int s = get_workspace(wfl * sizeof(float), &ws, 5);
+  int s = get_workspace(wfl * sizeof(float), &ws, 5, ST(stream));
   if (s) return s;
   float* W0 = (float*)ws;
   float* Kss = W0 + (size_t)B * T * (H + 1);
   float* mean_s = Kss + (size_t)B * H * H;
   float* scal = mean_s + (size_t)B * H;
   void* Lw = nullptr;
-  s = get_workspace((size_t)B * T * T * sizeof(float), &Lw, 6);
+  s = get_workspace((size_t)B * T * T * sizeof(float), &Lw, 6, ST(stream));
   if (s) return s;
   s = launch_bm_posterior_pack(x, B, T, xs, H, y, vol, vol_stride, W0, Kss, mean_s, nullptr, ST(stream));
   if (s) return s;
@@ -482,7 +510,7 @@ int volt_mvn_sample(const float* mean, const float* cov, const float* eps, int B
   VOLT_REQUIRE(mean && cov && eps && samples, "volt_mvn_sample: null pointer");
   VOLT_REQUIRE(B >= 1 && H >= 1 && S >= 1, "volt_mvn_sample: bad shape");
   void* Lc = nullptr;
-  int s = get_workspace((size_t)B * H * H * sizeof(float), &Lc, 7);
+  int s = get_workspace((size_t)B * H * H * sizeof(float), &Lc, 7, ST(stream));
   if (s) return s;
   s = volt_potrf(cov, (long long)H * H, H, nullptr, 0, B, H, jitter, 3, (float*)Lc, (long long)H * H, H, nullptr, info, stream);
   if (s) return s;
@@ -508,7 +536,7 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
   const size_t bn = (size_t)B * n, bn1 = (size_t)B * (n + 1);
   const size_t fl = bn + 3 * bn1 + bn + (size_t)B * VOLT_NSCALARS + (size_t)B * NSERIES + (size_t)(k > 0 ? k : 1) + (size_t)B;
   void* ws = nullptr;
-  int s = get_workspace(fl * sizeof(float), &ws, 8);
+  int s = get_workspace(fl * sizeof(float), &ws, 8, st);
   if (s) return s;
   float* Vt = (float*)ws;
   float* path = Vt + bn;

@@ -308,7 +308,7 @@ int launch_mll_batched_simt(MllParams p, cudaStream_t st) {
   if (grid < 1) grid = 1;
   const size_t per_cta = (size_t)p.Tp * p.Tp + (size_t)p.nb * NB * NB;
   void* ws = nullptr;
-  int s = get_workspace(per_cta * grid * sizeof(float), &ws, 0);
+  int s = get_workspace(per_cta * grid * sizeof(float), &ws, 0, st);
   if (s) return s;
   p.scratch = reinterpret_cast<float*>(ws);
   p.dinv = p.scratch + (size_t)grid * p.Tp * p.Tp;

@@ -523,13 +523,13 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   p.kind = mp.kind;
   const size_t tp2 = (size_t)p.Tp * p.Tp;
   void *w = nullptr, *u = nullptr, *aux = nullptr;
-  int s = get_workspace(tp2 * sizeof(float), &w, 9);
+  int s = get_workspace(tp2 * sizeof(float), &w, 9, st);
   if (s) return s;
-  s = get_workspace(tp2 * sizeof(float), &u, 10);
+  s = get_workspace(tp2 * sizeof(float), &u, 10, st);
   if (s) return s;
   p.trp_ld = (p.Tp + CM - 1) / CM + 1;
   const size_t aux_fl = (size_t)p.nb * NB * NB + 4 * (size_t)p.Tp + 16 + (size_t)p.nb * p.trp_ld;
-  s = get_workspace(aux_fl * sizeof(float), &aux, 11);
+  s = get_workspace(aux_fl * sizeof(float), &aux, 11, st);
   if (s) return s;
   p.W = (float*)w;
   p.Ut = (float*)u;

@@ -92,6 +92,7 @@ struct RolloutParams {
   float* samples;          // (B,S,H)
   int* info;               // (B,S) bit0: per-draw pivot failure, bit1: pred_cov needed jitter, bit2: not PSD after jitter
   int Hp;                  // padded tile row length (odd)
+  int b_offset;            // global index of series 0 of this launch (batches > 65535 series are launched in chunks)
 };
 
 int launch_mll_batched(MllParams p, cudaStream_t st);      // dispatches on the selected implementation

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
         if (p.eps) {
           e_n = ep[idx];
         } else {
-          if ((idx & 3) == 0) philox_normal4(p.seed, (uint32_t)b, (uint32_t)s, (uint32_t)(idx >> 2), zq);
+          if ((idx & 3) == 0) philox_normal4(p.seed, (uint32_t)(p.b_offset + b), (uint32_t)s, (uint32_t)(idx >> 2), zq);
           const int sel = idx & 3;
           e_n = sel == 0 ? zq[0] : sel == 1 ? zq[1] : sel == 2 ? zq[2] : zq[3];
         }
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
           const float d = (C0 + jit_total) - f2;
           if (!(d > 0.f)) bad = true;
           const float l = sqrtf(d);
-          const float e_n = p.eps ? ep[h] : philox_normal(p.seed, (uint32_t)b, (uint32_t)s, (uint32_t)h);
+          const float e_n = p.eps ? ep[h] : philox_normal(p.seed, (uint32_t)(p.b_offset + b), (uint32_t)s, (uint32_t)h);
           float mean = uz + (p.mean_test ? p.mean_test[(size_t)b * H + h] : 0.f);
           if (p.use_theta) mean -= p.theta * (mean - latent);
           out[h] = mean + fe + l * e_n;
@@ -410,6 +410,7 @@ int launch_rollout(RolloutParams p, cudaStream_t st) {
     RolloutParams q = p;
     const int nb = min(65535, p.B - b0);
     q.B = nb;
+    q.b_offset = p.b_offset + b0;   // Philox counters are keyed on the GLOBAL series index: chunks draw distinct normals
     q.ytrain = p.ytrain + (size_t)b0 * p.n;
     if (p.e_train) q.e_train = p.e_train + (size_t)b0 * (p.n + 1);
     if (p.ee_train) q.ee_train = p.ee_train + (size_t)b0 * (p.n + 1);

@@ -37,8 +37,13 @@ class _Adam:
             p.sub_((self.lr / bc1) * (m / denom))
 
 
-def _run(iteration, train_iters, printing, scal):
-    """Warm up eagerly (workspace allocation is not capturable), capture one iteration, replay the rest."""
+LARGE_PATH_T = 1536   # api.cu launch_mll_batched: a single series this long takes the multi-CTA path (chol_large.cu)
+
+
+def _run(iteration, train_iters, printing, scal, capturable=True):
+    """Warm up eagerly (workspace allocation is not capturable), capture one iteration, replay the rest.
+    capturable=False (the multi-CTA long-series path reads a failure flag back per factorisation attempt, which is illegal
+    during stream capture): every iteration is launched eagerly -- still device resident, no host synchronisation."""
     done = 0
     for _ in range(min(2, train_iters)):
         iteration()
@@ -48,16 +53,24 @@ def _run(iteration, train_iters, printing, scal):
     if done == train_iters:
         return
     graph = None
-    try:
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            iteration()
-        graph = g
-        done += 1  # capture does not execute; account for the replay below
-        graph.replay()
-    except Exception:  # noqa: BLE001  (capture unsupported: stay eager on the GPU)
-        graph = None
+    if capturable:
+        prev_stream = torch.cuda.current_stream()
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                iteration()
+            graph = g
+            done += 1  # capture does not execute; account for the replay below
+            graph.replay()
+        except Exception as exc:  # noqa: BLE001  (capture refused: stay eager on the GPU, and say so)
+            import warnings
+
+            graph = None
+            torch.cuda.set_stream(prev_stream)      # a failed capture_end leaves the side stream current
+            torch.cuda.synchronize()
+            warnings.warn(f"volt_b200.fused: CUDA-graph capture of the Adam iteration failed ({exc}); running eagerly",
+                          RuntimeWarning)
     while done < train_iters:
         if graph is not None:
             graph.replay()
@@ -96,7 +109,7 @@ def _fit_noise_ma(model, likelihood, train_x, target, lr, train_iters, printing)
         bad.add_(info.ne(0).to(torch.int32))
         opt.step([-(scal[0, S_DNOISE] * torch.sigmoid(raw))])   # d(-mll)/d raw_noise
 
-    _run(iteration, train_iters, printing, scal)
+    _run(iteration, train_iters, printing, scal, capturable=T < LARGE_PATH_T)
     if int(bad) != 0:
         raise ops.NotPSDError("training: covariance not positive definite after jitter retries")
     with torch.no_grad():
@@ -139,7 +152,7 @@ def _fit_bmgp(model, likelihood, train_x, target, lr, train_iters, printing):
         g_noise = d_noise * torch.sigmoid(raw_noise)
         opt.step([-g_noise.reshape(1), -g_vol.reshape(1)])
 
-    _run(iteration, train_iters, printing, scal)
+    _run(iteration, train_iters, printing, scal, capturable=T < LARGE_PATH_T)
     if int(bad) != 0:
         raise ops.NotPSDError("training: covariance not positive definite after jitter retries")
     with torch.no_grad():

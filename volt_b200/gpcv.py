@@ -43,7 +43,8 @@ def _running_std(y):
 
 def init_variational(x, y, vol0=0.2):
     """SingleTaskVariationalGP.initialize_variational_parameters, param="exp" (single_task_variational_gp.py:204-253).
-    x (n,), y (B,n) on the GPU -> (variational_mean (B,n), chol_variational_covar (B,n,n))."""
+    x (n,), y (B,n) on the GPU -> (variational_mean (B,n), chol_variational_covar (B,n,n), constant (B,)): the routine's last
+    line (:254) sets the ConstantMean of the prior to log(mean(running_std)), running_std after the [:10] patch."""
     B, n = y.shape
     rs = _running_std(y)
     rs[..., :10] = rs[..., 10:11]
@@ -57,31 +58,35 @@ def init_variational(x, y, vol0=0.2):
     Li, _, _ = ops.potrf(inner, check=False)
     S = Lk.unsqueeze(0) @ ops.potrs(Li, Lk.t().unsqueeze(0).expand(B, n, n).contiguous())
     S_root, _, _ = ops.potrf(S, check=False)                   # root_decomposition(method="cholesky")
-    return f, torch.tril(S_root) * 10.0
+    return f, torch.tril(S_root) * 10.0, rs.mean(-1).log()
 
 
 class _State:
     pass
 
 
-def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=False, return_state=False, use_graph=True):
-    """Batched LearnGPCV.  train_x (n,), train_y (B,n+1) or (n+1,) prices.  Returns pred_scale (B,n) on the GPU
+def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=False, return_state=False, use_graph=True,
+               returns=None):
+    """Batched LearnGPCV.  train_x (n,), train_y (B,n+1) or (n+1,) prices (or `returns` (B,n): the scaled returns themselves,
+    as example.ipynb cells 5-8 fit them).  Returns pred_scale (B,n) on the GPU
     (train_utils.py:62-67: `likelihood(model(train_x), return_gaussian=False).scale.mean(0)` over 10 function samples;
     eps (B,n,10) fixes their base normals).  One Adam iteration (12 launches) is captured in a CUDA graph and replayed."""
     dev = ops._dev()
     lib = _lib.load()
     x = ops._f32(train_x, dev).reshape(-1)
     n = x.numel()
-    py = ops._f32(train_y, dev).reshape(-1, n + 1)
-    B = py.shape[0]
-    y = scaled_returns(x, py).contiguous()
-    vm0, cv0 = init_variational(x, y)
+    if returns is None:
+        y = scaled_returns(x, ops._f32(train_y, dev).reshape(-1, n + 1)).contiguous()
+    else:
+        y = ops._f32(returns, dev).reshape(-1, n).contiguous()
+    B = y.shape[0]
+    vm0, cv0, c0 = init_variational(x, y)
     # flat parameter buffer: [variational_mean | chol_variational_covar | constant | raw_vol]  (model.parameters() order)
     nm, nc = B * n, B * n * n
     P = torch.empty(nm + nc + 2 * B, device=dev)
     P[:nm] = vm0.reshape(-1)
     P[nm:nm + nc] = cv0.reshape(-1)
-    P[nm + nc:nm + nc + B] = 0.0                                                   # ConstantMean
+    P[nm + nc:nm + nc + B] = c0                                                    # ConstantMean, set by the init (:254)
     P[nm + nc + B:] = math.log(0.2 / 0.8)                                          # BMKernel(vol=0.2): logit
     G = torch.zeros_like(P)
     M1 = torch.zeros_like(P)

@@ -67,7 +67,7 @@ class _VoltBase(ExactGP):
         out = _generate_prediction(self, test_x, pv, eps.t().contiguous(), None, 0.5, jitter=1e-6,
                                    train_x=self.train_x, train_y=self.train_y, log_vol_path=self.log_vol_path,
                                    train_inputs_for_mean=self.train_inputs[0])
-        return out.t()  # (H, n_sample)
+        return out.t().squeeze(-1)  # (H, n_sample); (H,) for n_sample == 1 -- the reference's trailing .squeeze(-1) (:97-99)
 
     def SamplePrediction(self, test_x, n_sample=1, return_vol=False):
         self.vol_model.eval()

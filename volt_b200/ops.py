@@ -171,6 +171,10 @@ def mll_grad(kind, x, gen, resid, noise, jitter=1e-6, max_tries=3, vol_mode=VOL_
         xb = int(xd.ndim > 1)
         if xb:
             xd = xd.reshape(-1, T)
+            if xd.shape[0] == 1:
+                xd = xd.expand(B, T).contiguous()
+            elif xd.shape[0] != B:
+                raise ValueError(f"a batched time grid needs one row per series: got {xd.shape[0]} rows for {B} series")
         _lib.check(lib.volt_mll_grad_vol(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(nz), nstride, B, T, float(jitter),
                                          int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), st), "volt_mll_grad_vol")
     elif kind == "bm":
@@ -198,6 +202,10 @@ class _ExactMLL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, kind, x, gen, resid, noise, jitter, vol_mode):
+        if not torch.is_tensor(noise):
+            noise = torch.as_tensor(noise, dtype=torch.float32)
+        if not torch.is_tensor(resid):
+            resid = torch.as_tensor(resid, dtype=torch.float32)
         out = mll_grad(kind, x, gen, resid, noise, jitter=jitter, vol_mode=vol_mode)
         sc = out["scalars"]
         ctx.kind, ctx.T, ctx.in_dev = kind, resid.shape[-1], resid.device
