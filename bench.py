@@ -3,21 +3,25 @@
 1024 synthetic stock-return series x T=512, exact batched MLL + gradients) on N B200s of one node.
 
     python bench.py --gpus 1 --steps 20 --warmup 5                      # our arm (CUDA path through the C ABI)
-    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # reference arm: CPU oracle port on host cores
+    python bench.py --impl reference --gpus 1 --steps 20 --warmup 5     # reference arm: CPU oracle port on host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...               # one rank per GPU, series-sharded (weak scaling)
 
 A "step" is one exact MLL + gradient evaluation for every series of the local batch (train_utils.py:247-250 per
-series): cumtrapz -> fused build + potrf + forward substitution + trtri (tr A^-1, alpha) -> scalar loss all-reduce.
+series): cumtrapz -> ONE kernel (fused build + potrf + forward substitution + trtri -> tr A^-1, alpha; likelihood
+transform, dMLL/draw_noise and the rank-local partial of the loss in its epilogue) -> scalar loss all-reduce (side
+stream).  The residual y - EWMA_k(y) is computed once outside the timed region in BOTH arms (it does not depend on the
+trained parameter; the reference recomputes it every iteration, 0.1 % of its step).
 `value` is timed with inputs resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks);
 `e2e` is the same metric through the host-buffer C-ABI call (H2D of x / vol / resid / noise and D2H of the per-series
-results inside the timed region).  Two secondary objects ride on the c2 line: `rollout` (c4 per-GPU share) and
-`long_series` (c5: one series of T = 8192, tensor-pipe roofline point).  Other workloads (--workload c1|c3) are for
-profiling, not bench lines.
+results inside the timed region; at N > 1 also the loss all-reduce).  Extra objects on the c2 line: `rollout` (c4 per-GPU
+share), `long_series` (c5: one series of T = 8192), each with its own roofline and CPU baseline; `gpu_torch_baseline`
+(stock torch on the same GPU: what the reference's `.cuda()` path runs); `peaks` (incl. a TF32 cuBLAS GEMM measured in
+this run).  Other workloads (--workload c1|c3) are for profiling, not bench lines.
 """
 import argparse
 import json
-import math
 import os
+import platform
 import sys
 import threading
 import time
@@ -34,6 +38,24 @@ WORKLOADS = {
 }
 K_EWMA = 25
 RAW_NOISE = 1e-5  # train_utils.py:222 sets the RAW noise to 1e-5 (noise = softplus(1e-5) + 1e-4 ~ 0.6933)
+L2_NOTE = "GPU arm: L2 flushed between timed iterations (256 MB write); CPU arm: working set (GBs) exceeds every cache"
+
+
+def config_of(desc, B, T):
+    """Identical in both arms (the driver compares them)."""
+    return dict(workload=desc, series_per_gpu=B, T=T, mean=f"ewma k={K_EWMA} (residual precomputed outside the timed region)",
+                raw_noise=RAW_NOISE, l2=L2_NOTE)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return platform.processor() or platform.machine()
 
 
 def peaks():
@@ -90,31 +112,114 @@ class ClockSampler(threading.Thread):
                     samples=len(s))
 
 
-def cpu_train_cov(x, vol, sample):
-    """VoltMagpie.py:46: the reference builds train_cov once per series and caches it (not part of a step)."""
+# ---------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_inputs(n_series, T, dt):
+    """Cached train_cov (VoltMagpie.py:46: built once per series, not part of a step) and the precomputed residual."""
     from oracle import volt_oracle as O
+    from volt_b200 import batched
 
-    return O.vol_kernel(x, vol[:sample])
+    import torch
+
+    x, vol, logy = batched.synth_series(n_series, T, dt)
+    K = O.vol_kernel(x, vol)
+    resid = logy - O.ewma(logy, K_EWMA)[..., :-1]
+    raw = torch.full((n_series,), RAW_NOISE)
+    return K, resid, raw
 
 
-def cpu_mll_grad_arm(K, logy, raw, sample, reps, threads):
-    """The reference's CPU path for one MLL+grad step per series (cached train_cov, EWMA mean recomputed every
-    iteration, Cholesky MLL, autograd backward) as restated by the oracle; batched over `sample` series."""
+def cpu_mll_grad_step(K, resid, raw, threads, chunk=256):
+    """The reference's CPU path for one MLL+grad step per series (cached train_cov, Cholesky MLL through
+    psd_safe_cholesky, autograd backward) as restated by the oracle; batched over the series in chunks of `chunk` (bounds
+    the host memory of the autograd graph).  Returns seconds."""
     import torch
 
     from oracle import volt_oracle as O
 
     torch.set_num_threads(threads)
-    ys = logy[:sample]
-    best = float("inf")
-    for _ in range(reps):
-        r = raw[:sample].clone().requires_grad_(True)
-        t0 = time.perf_counter()
-        mean = O.ewma(ys, K_EWMA)[..., :-1]
-        mll = O.exact_mll(K, ys - mean, O.noise_from_raw(r))
+    t0 = time.perf_counter()
+    for lo in range(0, K.shape[0], chunk):
+        r = raw[lo:lo + chunk].clone().requires_grad_(True)
+        mll = O.exact_mll(K[lo:lo + chunk], resid[lo:lo + chunk], O.noise_from_raw(r))
         (-mll.sum()).backward()
-        best = min(best, time.perf_counter() - t0)
-    return sample / best, best
+    return time.perf_counter() - t0
+
+
+# ---------------------------------------------------------------------------------------------- GPU comparators
+def measure_tf32_peak(dev, n=8192):
+    """cuBLAS TF32 GEMM (fp32 in, TF32 tensor-core math) on this GPU, in this run: the tensor-pipe peak for kind::tf32."""
+    import torch
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 60
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = e0.elapsed_time(e1) / reps
+        del a, b
+        fl = 2.0 * n ** 3
+        return dict(burst=fl / (best * 1e-3) / 1e12, sustained=fl / (sustained * 1e-3) / 1e12,
+                    how=f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS), best of 10 / {reps} back to back, this run")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def gpu_torch_baseline(xd, vd, resid, raw, T, reps=3):
+    """Stock torch on the same GPU -- what the reference runs when its drivers move the tensors with .cuda()
+    (GenerateMultiMeanPreds.py:92-96): dense cached K, torch.linalg.cholesky (cuSOLVER / MAGMA batched potrf),
+    triangular solve, log-det, autograd backward.  Same inputs, same step definition; ms per step (best of reps)."""
+    import math
+
+    import torch
+
+    B = vd.shape[0]
+    dx = xd[1] - xd[0]
+    w = dx * torch.ones_like(xd)
+    w[0] *= 0.5
+    w[-1] *= 0.5
+    V = torch.cumsum(w * vd * vd, -1)
+    idx = torch.arange(T, device=xd.device)
+    K = V[:, torch.minimum(idx[:, None], idx[None, :])]        # cached train_cov (VoltMagpie.py:46)
+    eye = torch.eye(T, device=xd.device)
+    best = float("inf")
+    for it in range(reps + 1):
+        r = raw.clone().requires_grad_(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        noise = torch.nn.functional.softplus(r) + 1e-4
+        A = K + noise[:, None, None] * eye
+        L = torch.linalg.cholesky(A)
+        z = torch.linalg.solve_triangular(L, resid.unsqueeze(-1), upper=False).squeeze(-1)
+        mll = -0.5 * ((z * z).sum(-1) + 2.0 * torch.diagonal(L, dim1=-2, dim2=-1).log().sum(-1) + T * math.log(2 * math.pi)) / T
+        (-mll.sum()).backward()
+        e1.record()
+        torch.cuda.synchronize()
+        if it > 0:
+            best = min(best, e0.elapsed_time(e1))
+        loss = float(-mll.sum())
+        del A, L, z, mll, r
+    del K
+    torch.cuda.empty_cache()
+    return dict(ms_per_step=best, value=B / (best * 1e-3), unit="evals/s", loss=loss,
+                what="stock torch on this GPU (reference's .cuda() path): cached dense K, torch.linalg.cholesky + "
+                     "solve_triangular + autograd backward, fp32, best of %d" % reps)
 
 
 def main():
@@ -124,10 +229,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=32, help="series timed on the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="series per CPU step (0 = the whole per-GPU batch on the reference arm, 64 for the in-line cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true", help="skip the secondary rollout-throughput measurement")
     ap.add_argument("--no-long", action="store_true", help="skip the secondary long-series (c5) measurement")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-torch-on-GPU comparator")
     args = ap.parse_args()
 
     import torch
@@ -142,24 +248,21 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        from volt_b200 import batched
-
-        x, vol, logy = batched.synth_series(args.cpu_sample, T, dt)
-        raw = torch.full((args.cpu_sample,), RAW_NOISE)
-        K = cpu_train_cov(x, vol, args.cpu_sample)
-        for _ in range(max(args.warmup, 2)):
-            cpu_mll_grad_arm(K, logy, raw, args.cpu_sample, 1, threads)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            cpu_mll_grad_arm(K, logy, raw, args.cpu_sample, 1, threads)
-        el = time.perf_counter() - t0
-        value = args.cpu_sample * args.steps / el
-        sample = f"{args.cpu_sample} series x T={T} per step (of {B} per GPU), batched torch CPU"
+        n = args.cpu_sample if args.cpu_sample > 0 else B
+        K, resid, raw = cpu_inputs(n, T, dt)
+        for _ in range(max(args.warmup, 1)):
+            cpu_mll_grad_step(K, resid, raw, threads)
+        times = [cpu_mll_grad_step(K, resid, raw, threads) for _ in range(args.steps)]
+        el = sum(times)
+        value = n * args.steps / el
+        sample = (f"{n} of {B} series x T={T} per step, batched torch CPU (chunks of 256), {threads} threads on {cpu_model()}; "
+                  f"mean of {args.steps} steps (best step {n / min(times):.0f} evals/s, worst {n / max(times):.0f})")
         line = dict(impl="reference", metric="MLL+grad evals/sec", value=value, unit="evals/s", n_gpus=args.gpus,
                     steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps, higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=desc, series_per_step=args.cpu_sample, T=T, mean="ewma k=25", raw_noise=RAW_NOISE),
-                    cpu_baseline=dict(value=value, unit="evals/s", cores=threads, kind="port", sample=sample),
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config_of(desc, B, T),
+                    series_per_step=n, cpu_model=cpu_model(),
+                    cpu_baseline=dict(value=value, unit="evals/s", cores=threads, kind="port", sample=sample,
+                                      best_step_value=n / min(times)),
                     e2e=dict(value=value, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line), flush=True)
         return
@@ -189,7 +292,7 @@ def main():
     # weak scaling: every rank owns B series; series b of rank r is global series r*B + b
     x, vol, logy = batched.synth_series(B, T, dt, start=rank * B)
     xd, vd, yd = x.to(dev), vol.to(dev), logy.to(dev)
-    _, resid = ops.ma_mean("ewma", yd, K_EWMA, want_resid=True)
+    _, resid = ops.ma_mean("ewma", yd, K_EWMA, want_resid=True)     # outside the timed region in both arms
     raw = torch.full((B,), RAW_NOISE, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
@@ -198,12 +301,12 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         out = step()
+    float(out["loss"])
     torch.cuda.synchronize()
     assert int(out["info"].abs().sum()) == 0, "Cholesky failure on the synthetic workload"
 
-    # kernel-only timing of the dominant kernel (mll_batched_kernel) through the device-pointer C-ABI entry
-    noise = batched.noise_from_raw(raw)
     lib = _lib.load()
+    noise = batched.noise_from_raw(raw)
     scal = torch.empty(B, 16, device=dev)
     alpha = torch.empty(B, T, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
@@ -214,38 +317,56 @@ def main():
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # K timed steps.  The all-reduce of step s runs on a side stream under step s + 1; the end event of a step is
+    # recorded after the current stream has waited for the PREVIOUS step's collective (the last step waits for its own),
+    # so every collective completes inside a timed region.
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = _lib.launch_count()
+    prev = None
     for s in range(args.steps):
         flush.zero_()  # evict L2 between timed iterations (not timed)
         ev[s][0].record()
         out = step()
+        if prev is not None:
+            prev.wait()
+        if s == args.steps - 1:
+            out["loss"].wait()
         ev[s][1].record()
+        prev = out["loss"]
     torch.cuda.synchronize()
     launches = _lib.launch_count() - l0
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     loss = float(out["loss"])
 
-    # dominant-kernel duration, measured live (same stream, CUDA events, L2 flushed)
+    # dominant-kernel duration, measured live (same stream, CUDA events, L2 flushed): the fused-step kernel itself
+    loss_dev = torch.empty(1, device=dev)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for s in range(args.steps):
         flush.zero_()
         kev[s][0].record()
-        _lib.check(lib.volt_mll_grad_vol(xd.data_ptr(), 0, vd.data_ptr(), 1, resid.data_ptr(), noise.data_ptr(), 1, B, T, 1e-6, 3,
-                                         scal.data_ptr(), alpha.data_ptr(), info.data_ptr(), st), "volt_mll_grad_vol")
+        _lib.check(lib.volt_mll_grad_vol_raw(xd.data_ptr(), 0, vd.data_ptr(), 1, resid.data_ptr(), raw.data_ptr(), 1, B, T, 1e-6, 3,
+                                             scal.data_ptr(), alpha.data_ptr(), info.data_ptr(), loss_dev.data_ptr(), st),
+                   "volt_mll_grad_vol_raw")
         kev[s][1].record()
     torch.cuda.synchronize()
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
 
-    # end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region)
+    # end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region); at N > 1 the
+    # step also all-reduces the loss (host scalar -> device -> NCCL -> host), like the device-resident step
     hx, hv, hr = x.pin_memory(), vol.pin_memory(), resid.cpu().pin_memory()
     hn = noise.cpu().pin_memory()
     hs = torch.empty(B, 16).pin_memory()
     hi = torch.empty(B, dtype=torch.int32).pin_memory()
+    e2e_loss = torch.zeros(1, device=dev)
 
     def e2e_step():
         _lib.check(lib.volt_mll_grad_vol_host(hx.data_ptr(), hv.data_ptr(), hr.data_ptr(), hn.data_ptr(), 1, B, T, 1e-6, 3,
                                               hs.data_ptr(), None, hi.data_ptr()), "volt_mll_grad_vol_host")
+        if world > 1:
+            e2e_loss.fill_(-float(hs[:, 0].sum()))
+            dist.all_reduce(e2e_loss)
+            return float(e2e_loss)
+        return -float(hs[:, 0].sum())
 
     for _ in range(3):
         e2e_step()
@@ -254,17 +375,23 @@ def main():
     for s in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_step()
+        e2e_total = e2e_step()
         e2e_t += time.perf_counter() - t0
     clocks = sampler.finish()
-    assert abs(float(hs[:, 0].sum()) + loss) < 1e-2 * abs(loss) + 1e-3 or world > 1
+    assert abs(e2e_total - loss) < 1e-2 * abs(loss) + 1e-3, (e2e_total, loss)
+
+    pk = peaks()
+    tf32 = measure_tf32_peak(dev) if rank == 0 else None
 
     # secondary metric of BASELINE.json's north_star: Monte-Carlo rollout throughput on the c4 per-GPU share
     # (512 series x 512 draws x 30 steps, T=256, EWMA k=25, Philox normals in-kernel); reported, not the headline
     roll = None
+    rB, rT, rS, rH = 512, 256, 512, 30
     if args.workload == "c2" and not args.no_rollout:
-        rB, rT, rS, rH = 512, 256, 512, 30
         rx, rvol, rlogy = batched.synth_series(rB, rT, dt, start=rank * rB)
         g = torch.Generator().manual_seed(1 + rank)
         rpv = (rvol[:, -1:, None] * torch.exp(0.1 * torch.randn(rB, rS, rH, generator=g))).to(dev)
@@ -274,6 +401,7 @@ def main():
         torch.cuda.synchronize()
         rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
         for a, b in rev:
+            flush.zero_()
             a.record()
             ops.rollout(rxd, ryd, rvd, rpv, eps=None, k=K_EWMA, seed=3, check=False)
             b.record()
@@ -285,9 +413,9 @@ def main():
     # secondary: config c5 of BASELINE.json -- ONE series of T = 8192 through the multi-CTA long-series path (the
     # tensor-pipe roofline point); reported, never allowed to break the headline line
     long_ms = 0.0
+    lT = 8192
     if args.workload == "c2" and not args.no_long:
         try:
-            lT = 8192
             lx, lvol, llogy = batched.synth_series(1, lT, dt, start=rank)
             _, lres = ops.ma_mean("ewma", llogy.to(dev), K_EWMA, want_resid=True)
             lnoise = batched.noise_from_raw(torch.full((1,), RAW_NOISE, device=dev))
@@ -307,64 +435,120 @@ def main():
             print(f"[bench] long-series measurement skipped: {exc}", file=sys.stderr)
             long_ms = 0.0
 
+    # stock torch on the same GPU (SURVEY 2.4's second bar), rank 0 at N = 1 only
+    torch_base = None
+    if rank == 0 and world == 1 and not args.no_torch_baseline:
+        try:
+            torch_base = gpu_torch_baseline(xd, vd, resid, raw, T)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] stock-torch GPU baseline skipped: {exc}", file=sys.stderr)
+
     t = torch.tensor([total_ms, e2e_t * 1e3, kern_ms, roll_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, kern_ms, roll_ms = (float(v) for v in t)
-    if roll_ms > 0:
-        roll = dict(metric="rollout step-samples/sec", value=512 * 512 * 30 * world / (roll_ms * 1e-3), unit="step-samples/s",
-                    ms_per_call=roll_ms, config="c4 per-GPU share: 512 series x 512 draws x 30 steps, T=256, ewma k=25, Philox in-kernel",
-                    path_samples_per_s=512 * 512 * world / (roll_ms * 1e-3))
     value = B * world * args.steps / (total_ms * 1e-3)
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
 
-    pk = peaks()
-    traffic = None  # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, committed)
+    traffic, traffic_src = None, None  # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, committed)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f).get(args.workload)
         if tj:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = tj.get("source", "profiles/traffic.json (one ncu --set full capture of this kernel)")
     # algorithmic work per eval: bytes 4 T^2 + 12 T (build fused into the factorisation),
     # flops 2 T^3 / 3 (potrf + trtri) + 4 T^2
     bytes_per_eval = 4.0 * T * T + 12.0 * T
     flops_per_eval = 2.0 * T ** 3 / 3.0 + 4.0 * T * T
     ach_gbs = bytes_per_eval * B / (kern_ms * 1e-3) / 1e9
     ach_tf = flops_per_eval * B / (kern_ms * 1e-3) / 1e12
+    tf32_peak = tf32["sustained"] if tf32 else None
     line = dict(
         metric="MLL+grad evals/sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-        data="synthetic",
-        config=dict(workload=desc, series_per_gpu=B, T=T, mean=f"ewma k={K_EWMA}", raw_noise=RAW_NOISE,
-                    l2="flushed between timed iterations (256 MB write)", loss=loss),
-        e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=int((T + 2 * B * T + B) * 4),
-                 d2h_bytes_per_step=int(B * 16 * 4 + B * 4)),
+        data="synthetic", config=config_of(desc, B, T), loss=loss,
+        e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=int((T + 2 * B * T + B) * 4 + (4 if world > 1 else 0)),
+                 d2h_bytes_per_step=int(B * 16 * 4 + B * 4 + (4 if world > 1 else 0)),
+                 collective=("loss all-reduce inside the timed step" if world > 1 else "none (one rank)")),
         gpu_launches=int(launches),
         clocks=clocks,
-        rollout=roll,
-        long_series=(dict(metric="MLL+grad evals/sec, one series of T=8192 (config c5, multi-CTA path)", ms_per_eval=long_ms,
-                          value=1e3 / long_ms, unit="evals/s", n_gpus=1,
-                          roofline=dict(bound="tensor", achieved=(2.0 * 8192 ** 3 / 3.0 + 4.0 * 8192 ** 2) / (long_ms * 1e-3) / 1e12,
-                                        peak=peaks()["tf"], unit="TFLOP/s",
-                                        frac=(2.0 * 8192 ** 3 / 3.0 + 4.0 * 8192 ** 2) / (long_ms * 1e-3) / 1e12 / peaks()["tf"],
-                                        note="algorithmic flops (potrf + trtri); 3x are issued (3xTF32); peak = measured bf16 dense GEMM"))
-                     if long_ms > 0 else None),
+        peaks=dict(hbm_gbs=pk["hbm"], bf16_tflops_sustained=pk["tf"], source=pk["source"], tf32_tflops=tf32),
         roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=traffic,
-                      kernel="mll_batched_tc_kernel (+ cumtrapz_kernel, <1% of the time)", ms_per_launch=kern_ms, bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
-        roofline_tensor=dict(bound="tensor", achieved=ach_tf, peak=pk["tf"], unit="TFLOP/s", frac=ach_tf / pk["tf"],
-                             flops_per_eval=flops_per_eval, note="tcgen05 kind::tf32 3-pass split (hi*hi + hi*lo + lo*hi): 3x the algorithmic flops are issued on the tensor pipe; peak is the measured bf16 dense GEMM figure (nominal TF32 peak is half of bf16)"),
+                      traffic_source=traffic_src,
+                      kernel="mll_batched_tc_kernel (+ cumtrapz_kernel, <1% of the time)", ms_per_launch=kern_ms,
+                      bytes_per_eval=bytes_per_eval, peak_source=pk["source"]),
+        roofline_tensor=dict(bound="tensor", achieved=ach_tf, peak=tf32_peak, unit="TFLOP/s",
+                             frac=(ach_tf / tf32_peak if tf32_peak else None), issued_frac=(3.0 * ach_tf / tf32_peak if tf32_peak else None),
+                             flops_per_eval=flops_per_eval,
+                             note="peak = the TF32 cuBLAS GEMM measured in this run (sustained); algorithmic flops (potrf + trtri); "
+                                  "the tcgen05 kind::tf32 3-pass split (hi*hi + hi*lo + lo*hi) issues 3x of them (issued_frac)"),
+        gpu_torch_baseline=torch_base,
     )
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            cx, cv, cy = batched.synth_series(args.cpu_sample, T, dt)
-            craw = torch.full((args.cpu_sample,), RAW_NOISE)
-            cK = cpu_train_cov(cx, cv, args.cpu_sample)
-            cpu_mll_grad_arm(cK, cy, craw, args.cpu_sample, 2, threads)
-            v, best = cpu_mll_grad_arm(cK, cy, craw, args.cpu_sample, 5, threads)
-            line["cpu_baseline"] = dict(value=v, unit="evals/s", cores=threads, kind="port",
-                                        sample=f"{args.cpu_sample} of {B} series x T={T}, batched torch CPU, best of 5 "
-                                               f"({best * 1e3:.0f} ms per pass)")
+        from oracle import volt_oracle as O   # CPU baselines only (the checker / comparator, never the product path)
+
+        want_cpu = world == 1 and not args.no_cpu_baseline
+        if roll_ms > 0:
+            n_ss = rB * rS * rH
+            # 12 B per step-sample (pred_vol in, base normal in, sample out; the normals are generated in-kernel
+            # here: 8 B) + the per-series shared factor (4 T^2: build fused, written once to scratch)
+            r_bytes = 8.0 * n_ss + rB * 4.0 * rT * rT
+            r_gbs = r_bytes / (roll_ms * 1e-3) / 1e9
+            roll = dict(metric="rollout step-samples/sec", value=n_ss * world / (roll_ms * 1e-3), unit="step-samples/s",
+                        ms_per_call=roll_ms, path_samples_per_s=rB * rS * world / (roll_ms * 1e-3),
+                        config="c4 per-GPU share: 512 series x 512 draws x 30 steps, T=256, ewma k=25, Philox in-kernel, L2 flushed",
+                        roofline=dict(bound="hbm", achieved=r_gbs, peak=pk["hbm"], unit="GB/s", frac=r_gbs / pk["hbm"],
+                                      bytes_per_call=r_bytes, stream_only_gbs=8.0 * n_ss / (roll_ms * 1e-3) / 1e9,
+                                      note="algorithmic bytes: 8 B per step-sample (pred_vol in, sample out, normals in-kernel) "
+                                           "+ 4 T^2 per series for the shared factor; whole call (prep + rollout kernel)"))
+            if want_cpu:
+                cS, cB = 16, 2
+                cx, cvol, clogy = batched.synth_series(cB, rT, dt)
+                g = torch.Generator().manual_seed(1)
+                cpv = cvol[:, -1:, None] * torch.exp(0.1 * torch.randn(cB, cS, rH, generator=g))
+                ceps = torch.randn(cB, cS, rH, generator=g)
+                ctx = cx[-1] + cx[1] * torch.arange(1, rH + 1)
+                torch.set_num_threads(threads)
+                t0 = time.perf_counter()
+                for b in range(cB):
+                    px = torch.cat((clogy[b, :1], clogy[b])).exp()
+                    O.rollouts(cx, px, cvol[b].log(), ctx, cpv[b], ceps[b], K_EWMA)
+                cel = time.perf_counter() - t0
+                roll["cpu_baseline"] = dict(value=cB * cS * rH / cel, unit="step-samples/s", cores=threads, kind="port",
+                                            sample=f"{cB} series x {cS} draws x {rH} steps, T={rT} (re-factorisation per step, "
+                                                   f"rollout_utils.py:35), {cel:.1f} s on {cpu_model()}")
+        line["rollout"] = roll
+        long_obj = None
+        if long_ms > 0:
+            lfl = 2.0 * lT ** 3 / 3.0 + 4.0 * lT ** 2
+            l_tf = lfl / (long_ms * 1e-3) / 1e12
+            long_obj = dict(metric="MLL+grad evals/sec, one series of T=8192 (config c5, multi-CTA path)", ms_per_eval=long_ms,
+                            value=1e3 / long_ms, unit="evals/s", n_gpus=1,
+                            roofline=dict(bound="tensor", achieved=l_tf, peak=tf32_peak, unit="TFLOP/s",
+                                          frac=(l_tf / tf32_peak if tf32_peak else None),
+                                          issued_frac=(3.0 * l_tf / tf32_peak if tf32_peak else None),
+                                          note="algorithmic flops (potrf + trtri); 3x are issued (3xTF32); peak = TF32 cuBLAS GEMM measured in this run"))
+            if want_cpu:
+                lx, lvol, llogy = batched.synth_series(1, lT, dt)
+                lK = O.vol_kernel(lx, lvol)
+                lres = llogy - O.ewma(llogy, K_EWMA)[..., :-1]
+                lraw = torch.full((1,), RAW_NOISE)
+                cpu_mll_grad_step(lK, lres, lraw, threads)
+                cel = min(cpu_mll_grad_step(lK, lres, lraw, threads) for _ in range(2))
+                long_obj["cpu_baseline"] = dict(value=1.0 / cel, unit="evals/s", cores=threads, kind="port",
+                                                sample=f"the same series, torch CPU (Cholesky MLL + autograd backward), best of 2 "
+                                                       f"({cel:.2f} s) on {cpu_model()}")
+        line["long_series"] = long_obj
+        if want_cpu:
+            n = args.cpu_sample if args.cpu_sample > 0 else 64
+            cK, cres, craw = cpu_inputs(n, T, dt)
+            cpu_mll_grad_step(cK, cres, craw, threads)
+            times = [cpu_mll_grad_step(cK, cres, craw, threads) for _ in range(5)]
+            line["cpu_baseline"] = dict(value=n / min(times), unit="evals/s", cores=threads, kind="port", cpu_model=cpu_model(),
+                                        sample=f"{n} of {B} series x T={T}, batched torch CPU, best of 5 ({min(times) * 1e3:.0f} ms per "
+                                               f"pass; mean {n * 5 / sum(times):.0f} evals/s)")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

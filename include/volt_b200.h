@@ -55,6 +55,8 @@ extern "C" {
 #define VOLT_S_JITTER 7    /* jitter the psd_safe_cholesky policy had to add (0 if none) */
 #define VOLT_S_Z2Z2 8      /* |L^-1 rhs2|^2   (second right-hand side, used by the rollout) */
 #define VOLT_S_Z1Z2 9      /* (L^-1 r).(L^-1 rhs2) */
+#define VOLT_S_DRAW 10     /* d MLL / d raw_noise = VOLT_S_DNOISE * sigmoid(raw_noise)   (volt_mll_grad_vol_raw only) */
+#define VOLT_S_NOISE 11    /* noise = softplus(raw_noise) + 1e-4                          (volt_mll_grad_vol_raw only) */
 
 /* moving-average mean families (voltron/means/EWMA.py) */
 #define VOLT_MA_EWMA 0
@@ -117,6 +119,18 @@ int volt_ma_mean(const float* y, int S, int T, int k, int kind, float theta, con
 int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* noise,
                       int noise_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
                       void* stream);
+
+/* The whole training step of the data model in one launch:  voltron/train_utils.py:247-250 with the likelihood's parameter
+ * transform ([GPyTorch] GaussianLikelihood: noise = softplus(raw_noise) + 1e-4, the transform `voltron.likelihood.raw_noise`
+ * goes through at train_utils.py:222,249) and the reduction to the scalar loss folded into the kernel.
+ * raw_noise (B) with stride raw_stride (0 = shared).  Besides the outputs of volt_mll_grad_vol:
+ *   scalars[b][VOLT_S_DRAW] = d MLL_b / d raw_noise_b, scalars[b][VOLT_S_NOISE] = noise_b,
+ *   loss_out[0] (or NULL) = -sum_b MLL_b, summed in a fixed order by the last CTA to finish (bitwise reproducible): the
+ *   rank-local partial of the series-sharded loss, all-reduced by the caller (volt_b200/batched.py).
+ * An empty batch writes loss_out[0] = 0. */
+int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
+                          int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                          float* loss_out, void* stream);
 
 /* Same for the vol model BMGP (A = scale_b * min(x_i, x_j) + noise_b I)  -- voltron/train_utils.py:86-90,
  * voltron/models/BMGP.py:20-28.  x (T) shared grid. */

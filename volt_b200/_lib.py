@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VOLT_B200_LIB") or os.path.join(HERE, "csrc", "libvolt_b200.so")
 
 VOLT_NSCALARS = 16
-S_MLL, S_DNOISE, S_LOGDET, S_INVQUAD, S_TRINV, S_ALAL, S_ALR, S_JITTER, S_Z2Z2, S_Z1Z2 = range(10)
+S_MLL, S_DNOISE, S_LOGDET, S_INVQUAD, S_TRINV, S_ALAL, S_ALR, S_JITTER, S_Z2Z2, S_Z1Z2, S_DRAW, S_NOISE = range(12)
 MA_EWMA, MA_DEWMA, MA_TEWMA, MA_MEANREVERT, MA_GIVEN = range(5)
 VOL_RAW, VOL_SIGMA, VOL_LOGSIGMA = 0, 1, 2
 
@@ -31,6 +31,8 @@ _SIGS = {
     "volt_ma_mean": (c_int, [_fp, c_int, c_int, c_int, c_int, c_float, _fp, _fp, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_vol": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp,
                                   c_void_p]),
+    "volt_mll_grad_vol_raw": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp,
+                                      c_void_p]),
     "volt_mll_grad_bm": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_bm_inv": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_dense": (c_int, [_fp, c_longlong, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp,

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from ._lib import S_DNOISE, S_MLL
+from ._lib import S_DRAW, S_MLL
 
 
 def shard_bounds(n_items, rank, world):
@@ -29,7 +29,8 @@ def dist_info():
 
 
 def all_reduce_sum(t):
-    """Sum a (scalar) tensor over ranks: the single collective of the batched MLL path."""
+    """Sum a (scalar) tensor over ranks: the single collective of the batched MLL path (blocking form; the training step
+    uses the asynchronous one below)."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -42,19 +43,66 @@ def noise_from_raw(raw_noise):
     return F.softplus(raw_noise) + 1e-4
 
 
+class PendingLoss:
+    """The all-reduced scalar loss of one step.  The collective runs on a side stream so that the next step's kernels are
+    not held back by it (nor by the slowest rank); `wait()` orders the CURRENT stream after it and returns the 0-dim
+    tensor; `float(loss)` / `loss.item()` do that and read it back."""
+
+    def __init__(self, tensor, event):
+        self._t, self._ev = tensor, event
+
+    def wait(self):
+        if self._ev is not None:
+            torch.cuda.current_stream().wait_event(self._ev)
+            self._ev = None
+        return self._t
+
+    def item(self):
+        return self.wait().item()
+
+    def __float__(self):
+        return float(self.wait())
+
+
+_side = {}   # device index -> (side stream, ring of loss buffers, cursor)
+_RING = 8
+
+
+def _async_loss_all_reduce(partial):
+    """partial: 0-dim / (1,) CUDA tensor produced on the current stream.  World size 1: returned as is."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return PendingLoss(partial.reshape(()), None)
+    dev = partial.device.index
+    if dev not in _side:
+        _side[dev] = [torch.cuda.Stream(device=dev), torch.empty(_RING, device=partial.device), 0]
+    side, ring, cur = _side[dev]
+    _side[dev][2] = (cur + 1) % _RING
+    buf = ring[cur:cur + 1]
+    produced = torch.cuda.Event()
+    produced.record()
+    with torch.cuda.stream(side):
+        side.wait_event(produced)
+        buf.copy_(partial.reshape(1))          # the step's own buffer is free to be overwritten by the next step
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        done = torch.cuda.Event()
+        done.record()
+    return PendingLoss(buf.reshape(()), done)
+
+
 def mll_and_grad(x, vol, resid, raw_noise, jitter=1e-6, check=False):
-    """One MLL + gradient evaluation for each of the B local series (train_utils.py:247-250 per series).
+    """One MLL + gradient evaluation for each of the B local series (train_utils.py:247-250 per series): ONE launch
+    (plus the prefix-sum kernel) -- the likelihood's softplus transform, dMLL/draw_noise and the rank-local partial of the
+    loss are produced by the kernel's epilogue (volt_mll_grad_vol_raw); the 4-byte all-reduce runs on a side stream.
 
     x (T,), vol (B,T), resid (B,T) = log y - mean, raw_noise (B,).  Returns dict of CUDA tensors:
-    mll (B,), draw_noise (B,) = dMLL/draw_noise, alpha (B,T) (dMLL/dmean = alpha/T), info (B,), loss = -sum mll
-    all-reduced over ranks (a 0-dim tensor)."""
-    noise = noise_from_raw(raw_noise)
-    out = ops.mll_grad("vol", x, vol, resid, noise, jitter=jitter, check=check)
+    mll (B,), draw_noise (B,) = dMLL/draw_noise, alpha (B,T) (dMLL/dmean = alpha/T), info (B,), scalars (B,16), and
+    loss = -sum mll over ALL ranks as a PendingLoss (float(loss) / loss.wait())."""
+    out = ops.mll_step("vol", x, vol, resid, raw_noise, jitter=jitter, check=check)
     sc = out["scalars"]
-    mll = sc[:, S_MLL]
-    loss = all_reduce_sum(-mll.sum())
-    return dict(mll=mll, draw_noise=sc[:, S_DNOISE] * torch.sigmoid(raw_noise.to(sc.device)), alpha=out["alpha"],
-                info=out["info"], loss=loss, scalars=sc)
+    return dict(mll=sc[:, S_MLL], draw_noise=sc[:, S_DRAW], alpha=out["alpha"], info=out["info"],
+                loss=_async_loss_all_reduce(out["loss"]), scalars=sc)
 
 
 def train_noise(x, vol, logy, k=25, mean_func="ewma", train_iters=300, lr=0.1, raw_init=1e-5):

@@ -35,7 +35,7 @@ int check_cuda(cudaError_t e, const char* what) {
 // Work submitted to one stream is ordered, so kernels that share an arena never overlap; two streams (or the library's own
 // copy / compute streams behind the host-buffer entry) get separate arenas and therefore cannot race on the scratch.
 // Grown on demand (device-wide synchronisation before the old block is freed), released by volt_release_workspaces().
-constexpr int kSlots = 13;
+constexpr int kSlots = 16;
 struct Ws {
   int slot = 0;
   cudaStream_t stream = nullptr;
@@ -45,7 +45,8 @@ struct Ws {
 static std::vector<Ws> g_ws[16];
 static std::mutex g_mu;
 
-int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream) {
+int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream, int* created) {
+  if (created) *created = 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || slot < 0 || slot >= kSlots) {
     set_error("get_workspace: bad device/slot");
@@ -55,13 +56,26 @@ int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream) {
   Ws* w = nullptr;
   for (Ws& e : g_ws[dev])
     if (e.slot == slot && e.stream == stream) { w = &e; break; }
+  if (bytes == 0) bytes = 256;
+  if (!w || w->bytes < bytes) {
+    // Nothing may be allocated while `stream` is being captured into a CUDA graph (torch.cuda.graph captures on a side
+    // stream of its own).  A graph keeps the pointers it was captured with wherever it is replayed, so the capture
+    // borrows an arena that an eager warm-up call has already created for this slot: replays then share that arena with
+    // eager calls on the warm-up stream, which is also where callers replay (stream order keeps them apart).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+      for (Ws& e : g_ws[dev])
+        if (e.slot == slot && e.bytes >= bytes) { *ptr = e.ptr; return VOLT_OK; }
+      set_error("workspace (slot %d, %zu bytes) cannot be created during stream capture: run the call once eagerly first", slot, bytes);
+      return VOLT_ERR_ALLOC;
+    }
+  }
   if (!w) {
     g_ws[dev].emplace_back();
     w = &g_ws[dev].back();
     w->slot = slot;
     w->stream = stream;
   }
-  if (bytes == 0) bytes = 256;
   if (w->bytes < bytes) {
     if (w->ptr) {
       cudaDeviceSynchronize();
@@ -77,6 +91,7 @@ int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream) {
       return VOLT_ERR_ALLOC;
     }
     w->bytes = want;
+    if (created) *created = 1;
   }
   *ptr = w->ptr;
   return VOLT_OK;
@@ -152,6 +167,26 @@ __global__ void gather_scalar_kernel(const float* __restrict__ scalars, int B, i
 int launch_gather_scalar(const float* scalars, int B, int idx, float* out, cudaStream_t st) {
   gather_scalar_kernel<<<(B + 127) / 128, 128, 0, st>>>(scalars, B, idx, out);
   return check_cuda(cudaGetLastError(), "gather_scalar_kernel");
+}
+
+// [GPyTorch] GaussianLikelihood noise transform and the step's scalar outputs for the kernels that do not fuse them
+// (SIMT A/B kernel, multi-CTA long-series path): same arithmetic and summation order as the fused epilogue of chol_tc.cu.
+__global__ void noise_from_raw_kernel(const float* __restrict__ raw, int stride, int B, float* __restrict__ noise) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) noise[b] = noise_from_raw_dev(raw[(size_t)b * stride]);
+}
+__global__ void __launch_bounds__(256) raw_finish_kernel(const float* __restrict__ raw, int stride, const float* __restrict__ noise,
+                                                         int B, float* __restrict__ scalars, float* __restrict__ loss_out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    float* o = scalars + (size_t)b * VOLT_NSCALARS;
+    o[VOLT_S_DRAW] = o[VOLT_S_DNOISE] * sigmoid_dev(raw[(size_t)b * stride]);
+    o[VOLT_S_NOISE] = noise[b];
+    acc += o[VOLT_S_MLL];
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0 && loss_out) loss_out[0] = -tot;
 }
 
 // implementation switch for the batched MLL kernel: 1 = tcgen05 (default), 0 = SIMT fp32 (kept for A/B measurement)
@@ -278,6 +313,54 @@ int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_m
   p.kind = KIND_VOL;
   p.V = (const float*)V;
   return launch_mll_batched(p, ST(stream));
+}
+
+int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
+                          int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                          float* loss_out, void* stream) {
+  if (B == 0) {   // empty shard: the step's partial loss is 0
+    if (loss_out) VOLT_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
+    return VOLT_OK;
+  }
+  VOLT_REQUIRE(x && vol && resid && raw_noise && scalars, "volt_mll_grad_vol_raw: null pointer");
+  VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol_raw: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
+  cudaStream_t st = ST(stream);
+  void* V = nullptr;
+  int s = get_workspace((size_t)B * T * sizeof(float), &V, 1, st);
+  if (s) return s;
+  void* aux = nullptr;   // [0] completion counter of the fused loss reduction | [64...] noise (B) for the unfused kernels
+  int created = 0;
+  s = get_workspace(256 + (size_t)B * sizeof(float), &aux, 13, st, &created);
+  if (s) return s;
+  if (created) VOLT_CUDA(cudaMemsetAsync(aux, 0, 256, st));
+  s = launch_cumtrapz(x, x_batched, vol, B, T, vol_mode, 1, (float*)V, st);
+  if (s) return s;
+  if (g_mll_impl < 0) {
+    const char* e = getenv("VOLT_MLL_IMPL");
+    g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
+  }
+  const bool fused = g_mll_impl && !(T >= 1536 && B <= 16);
+  if (fused) {
+    MllParams p = base_params(B, T, resid, nullptr, 0, jitter, max_tries, scalars, alpha, info);
+    p.kind = KIND_VOL;
+    p.V = (const float*)V;
+    p.raw_noise = raw_noise;
+    p.raw_stride = raw_stride;
+    p.loss_out = loss_out;
+    p.done_counter = (unsigned int*)aux;
+    return launch_mll_batched_tc(p, st);
+  }
+  float* noise = (float*)aux + 64;
+  noise_from_raw_kernel<<<(B + 127) / 128, 128, 0, st>>>(raw_noise, raw_stride, B, noise);
+  s = check_cuda(cudaGetLastError(), "noise_from_raw_kernel");
+  if (s) return s;
+  MllParams p = base_params(B, T, resid, noise, 1, jitter, max_tries, scalars, alpha, info);
+  p.kind = KIND_VOL;
+  p.V = (const float*)V;
+  s = launch_mll_batched(p, st);
+  if (s) return s;
+  raw_finish_kernel<<<1, 256, 0, st>>>(raw_noise, raw_stride, noise, B, scalars, loss_out);
+  return check_cuda(cudaGetLastError(), "raw_finish_kernel");
 }
 
 int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise, int noise_stride,

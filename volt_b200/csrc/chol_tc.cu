@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
       }
     }
     const float sc = (p.kind == KIND_BM) ? p.scale[(size_t)b * p.scale_stride] : 1.f;
-    const float dadd0 = p.diag_add ? p.diag_add[(size_t)b * p.diag_stride] : 0.f;
+    const float dadd0 = p.raw_noise ? noise_from_raw_dev(p.raw_noise[(size_t)b * p.raw_stride])
+                                    : (p.diag_add ? p.diag_add[(size_t)b * p.diag_stride] : 0.f);
     const float* rb = p.resid ? p.resid + (size_t)b * T : nullptr;
     const float* rb2 = p.resid2 ? p.resid2 + (size_t)b * T : nullptr;
 
@@ -371,7 +372,9 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
         o[1] = 0.5f * (alal - tr_inv) / Tf;
         o[2] = logdet; o[3] = inv_quad; o[4] = tr_inv; o[5] = alal; o[6] = alr; o[7] = jit_used;
         o[8] = sz22; o[9] = sz12;
-        for (int q = 10; q < NSCALARS; ++q) o[q] = 0.f;
+        o[10] = p.raw_noise ? o[1] * sigmoid_dev(p.raw_noise[(size_t)b * p.raw_stride]) : 0.f;   // dMLL/draw_noise (softplus' = sigmoid)
+        o[11] = p.raw_noise ? noise_from_raw_dev(p.raw_noise[(size_t)b * p.raw_stride]) : 0.f;
+        for (int q = 12; q < NSCALARS; ++q) o[q] = 0.f;
       }
       if (p.info) p.info[b] = fail;
     }
@@ -397,6 +400,28 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
     __syncthreads();
   }
 
+  if (p.loss_out) {
+    // scalar loss of the training step, -sum_b MLL_b, without a second launch: the last CTA to get here sums the per-series
+    // values in a fixed order (thread t takes b = t, t + 256, ...; then the block reduction), so the result does not
+    // depend on which CTA happens to be last.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int ticket = atomicAdd(p.done_counter, 1u);
+      *c.flag = (ticket == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (*c.flag) {
+      __threadfence();
+      float acc = 0.f;
+      for (int b = tid; b < p.B; b += NT) acc += __ldcg(p.scalars + (size_t)b * NSCALARS);
+      const float tot = block_sum(acc, c.red);
+      if (tid == 0) {
+        p.loss_out[0] = -tot;
+        *p.done_counter = 0u;   // ready for the next launch on this stream
+      }
+    }
+  }
 #ifdef VOLT_PROFILE
   TICK(11);
   if (tid == 0 && blockIdx.x == 0 && p.z_out == nullptr && p.alpha) {

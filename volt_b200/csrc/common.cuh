@@ -26,7 +26,7 @@ int check_cuda(cudaError_t e, const char* what);
   } while (0)
 
 // Cached workspace, one arena per (device, slot, stream): grown on demand, released by volt_release_workspaces().
-int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream);
+int get_workspace(size_t bytes, void** ptr, int slot, cudaStream_t stream, int* created = nullptr);
 int sm_count();
 int device_slot();   // current CUDA device clamped to [0, 16): index of the per-device caches (function attributes, streams)
 

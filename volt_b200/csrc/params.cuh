@@ -33,7 +33,16 @@ struct MllParams {
   const float* vol_in; const float* x_in; int x_batched, vol_mode;
   const int* ready; int ready_from;
   int* ready_timeout; long long ready_spins;   // give up after ready_spins polls: *ready_timeout = 1, the CTA stops (the host re-runs)
+  // fused training-step epilogue (tensor-core batched kernel; volt_mll_grad_vol_raw): the diagonal term is the GaussianLikelihood
+  // noise softplus(raw_noise) + 1e-4 evaluated in-kernel, scalars[VOLT_S_DRAW] = dMLL/draw_noise, scalars[VOLT_S_NOISE] = noise,
+  // and the last CTA to finish writes loss_out[0] = -sum_b MLL_b, summed in a fixed order (bitwise reproducible).
+  const float* raw_noise; int raw_stride;
+  float* loss_out; unsigned int* done_counter;
 };
+
+// [GPyTorch] GaussianLikelihood / GreaterThan(1e-4): noise = softplus(raw_noise) + 1e-4 (torch's softplus: beta 1, threshold 20)
+__device__ __forceinline__ float noise_from_raw_dev(float raw) { return (raw > 20.f ? raw : log1pf(expf(raw))) + 1e-4f; }
+__device__ __forceinline__ float sigmoid_dev(float raw) { return 1.f / (1.f + expf(-raw)); }
 
 // CumTrapz of one series by one warp (VolKernel.py:4-10).  torch.cumsum on CPU accumulates float32 data in a double
 // accumulator and rounds each prefix to float32; same here (per-lane sequential double sums + a warp scan of the lane

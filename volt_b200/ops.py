@@ -195,6 +195,45 @@ def mll_grad(kind, x, gen, resid, noise, jitter=1e-6, max_tries=3, vol_mode=VOL_
     return dict(scalars=scal, alpha=alpha, info=info)
 
 
+def mll_step(kind, x, gen, resid, raw_noise, jitter=1e-6, max_tries=3, vol_mode=VOL_SIGMA, check=True, want_alpha=True):
+    """The training step of the data model in one launch (volt_mll_grad_vol_raw): like mll_grad(kind="vol") but takes the
+    RAW likelihood noise (train_utils.py:222) -- softplus + 1e-4 is applied in-kernel -- and additionally returns
+    scalars[:, S_DRAW] = dMLL/draw_noise and `loss` (1,) = -sum_b MLL_b of this batch (fixed summation order)."""
+    if kind != "vol":
+        raise ValueError("mll_step: only the Volatility-kernel data model has a fused training step")
+    dev = _dev()
+    lib = _lib.load()
+    r = _f32(resid, dev)
+    T = r.shape[-1]
+    r = r.reshape(-1, T)
+    B = r.shape[0]
+    raw = _f32(raw_noise, dev).reshape(-1)
+    rstride = 0 if raw.numel() == 1 else 1
+    if rstride and raw.numel() != B:
+        raise ValueError("raw_noise must be a scalar or have one entry per series")
+    g = _f32(gen, dev).reshape(-1, T)
+    if g.shape[0] != B:
+        g = g.expand(B, T).contiguous()
+    xd = _f32(x, dev)
+    xb = int(xd.ndim > 1)
+    if xb:
+        xd = xd.reshape(-1, T)
+        if xd.shape[0] == 1:
+            xd = xd.expand(B, T).contiguous()
+        elif xd.shape[0] != B:
+            raise ValueError(f"a batched time grid needs one row per series: got {xd.shape[0]} rows for {B} series")
+    scal = _empty((B, VOLT_NSCALARS), dev)
+    alpha = _empty((B, T), dev) if want_alpha else None
+    info = _empty((B,), dev, torch.int32)
+    loss = _empty((1,), dev)
+    _lib.check(lib.volt_mll_grad_vol_raw(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(raw), rstride, B, T, float(jitter),
+                                         int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), _stream()),
+               "volt_mll_grad_vol_raw")
+    if check:
+        _check_info(info, scal[:, S_JITTER], "exact MLL")
+    return dict(scalars=scal, alpha=alpha, info=info, loss=loss)
+
+
 class _ExactMLL(torch.autograd.Function):
     """-> per-series MLL (GPyTorch normalisation, / T).  Analytic backward:
     dMLL/dresid = -alpha/T, dMLL/dnoise = 1/2 (alpha.alpha - tr A^-1)/T, and for the BM kernel
