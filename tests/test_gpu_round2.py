@@ -182,7 +182,9 @@ def test_rollout_samples_elementwise(vb, n, S, H, k, mean_func):
     for b in range(2):
         want = O.rollouts(x.double(), px[b].double(), vol[b].log().double(), test_x.double(), pred_vol[b].double(),
                           eps[b].double(), k, mean_kind=mean_func)
-        assert_elementwise(out[b], want, 1e-3, 0.0, "sample")
+        # absolute floor: a log price may pass through zero (seeded series drift from log 10 to ~0), where a purely relative
+        # bound is meaningless; the arithmetic runs on values of the size of the training series
+        assert_elementwise(out[b], want, 1e-3, 2e-4 * float(logy[b].abs().max()), "sample")
         last = float(logy[b, -1])
         inc, inc_ref = out[b].double().cpu() - last, want - last
         # measured on the B200: max abs error of the increment 1.0e-4 (ewma), 2.1e-4 (tewma: 3e - 3ee + eee amplifies the
