@@ -27,3 +27,7 @@ for n, v in zip(names, a.tolist()):
 print(f"CTA 0 total: {tot / 1e6:.2f} M cycles for {-(-B // 444)} series")
 print("diagonal block (thread 0 = pivot warp): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
     ["pivot16 / LiT clear", "barrier after pivot", "panel solve", "trailing update", "inverse blocks"], dg)))
+tm = out["alpha"].reshape(-1)[20:28].cpu().tolist()
+print("gemm_tma (thread 0): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
+    ["call-start fence+sync", "issue (TMA wait-done, TMA, MMA) + loop", "wait TMA full", "wait MMA done(g-2)", "split + st", "fence + barrier",
+     "drain"], tm)))

@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(NT, 1) large_update256_kernel(LargeParams p, i
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
   float* Cm = mode ? p.Ut : p.W;
   uint8_t* RAW = c.X;
+  const int wu = uniform_warp_id();                     // MMA issue from one elected lane of warp 0, uniform operands (elect_one)
+  const uint32_t tmem_u = make_uniform(c.tmem), xb = s_u32(c.X);
   const int nk = (k_hi - k_lo) / 32;
   for (int t = blockIdx.x; t < ncol * nrow; t += gridDim.x) {
     const int r_base = row_lo + CM * (t / ncol);      // rows of the C tile
@@ -444,18 +446,21 @@ __global__ void __launch_bounds__(NT, 1) large_update256_kernel(LargeParams p, i
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (wu == 0) {
         tc_fence_after();
-        const uint64_t dbh = make_desc(s_u32(BH)), dbl = make_desc(s_u32(BL));
+        if (elect_one()) {
+          const uint64_t dbh = make_desc(xb + U2_B0 + h * U2_BSTAGE), dbl = make_desc(xb + U2_B0 + h * U2_BSTAGE + U2_BSTAGE / 2);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t adv = (uint64_t)(2 * ks);
-          const uint32_t ah = c.tmem + U2_A0 + 64 * h + 8 * ks, al = ah + 32;
-          umma_tf32_ts256(c.tmem + U2_ACC, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
-          umma_tf32_ts256(c.tmem + U2_ACC, ah, dbl + adv, 1u);
-          umma_tf32_ts256(c.tmem + U2_ACC, ah, dbh + adv, 1u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t adv = (uint64_t)(2 * ks);
+            const uint32_t ah = tmem_u + U2_A0 + 64 * h + 8 * ks, al = ah + 32;
+            umma_tf32_ts256(tmem_u + U2_ACC, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+            umma_tf32_ts256(tmem_u + U2_ACC, ah, dbl + adv, 1u);
+            umma_tf32_ts256(tmem_u + U2_ACC, ah, dbh + adv, 1u);
+          }
+          umma_commit(c.bar + h);
         }
-        umma_commit(c.bar + h);
+        __syncwarp();
       }
     }
     wait_mma2(c, (nk - 1) & 1);

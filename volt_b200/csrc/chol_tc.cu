@@ -15,6 +15,10 @@
 //             U[0:i, i] = -G^T Linv_ii^T                            K = 64
 // SIMT work that remains: the 64x64 diagonal potrf / trtri (chol_dev.cuh), the hi/lo split while staging operand
 // tiles, the forward substitution for z, and the reductions.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "chol_tc_dev.cuh"
 
 namespace volt {
@@ -65,9 +69,15 @@ static __device__ __noinline__ bool hostin_prologue(const int* ready, int* ready
   return true;
 }
 
-template <bool TRI, bool HOSTIN = false>
-__global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllParams p) {
-  constexpr uint32_t LOFF = TRI ? Y_L_OFF : L_OFF, CTOFF = TRI ? Y_CT_OFF : CT_OFF, VECOFF = TRI ? Y_VEC_OFF : VEC_OFF;
+// TMA = true: the "W" instance (two CTAs per SM): operand tiles of every GEMM loop arrive through the TMA unit (gemm_tma,
+// chol_tc_dev.cuh); shared-memory map and accumulator parking as in the three-CTA instance, 256 TMEM columns, one-pass TRSM.
+template <bool TRI, bool HOSTIN = false, bool TMA = false>
+__global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllParams p, const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB) {
+  static_assert(!(TRI && TMA), "the TMA instance is a two-CTA instance");
+  constexpr bool PARK = TRI || TMA;   // chunk-0 panel rows wait in the accumulator columns during the diagonal factorisation
+  constexpr uint32_t LOFF = TMA ? W_L_OFF : (TRI ? Y_L_OFF : L_OFF), CTOFF = TMA ? W_CT_OFF : (TRI ? Y_CT_OFF : CT_OFF);
+  constexpr uint32_t VECOFF = TMA ? W_VEC_OFF : (TRI ? Y_VEC_OFF : VEC_OFF);
   constexpr uint32_t XTMP = TRI ? Y_TMP : X_TMP, TCOLS = TRI ? T3_COLS : TM_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw;
@@ -103,9 +113,21 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(s_tmem_p)), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  TmaPipe tp;
+  tp.full = reinterpret_cast<uint64_t*>(c.red + 44);
+  tp.done = tp.full + W_RING;
+  tp.g = 0;
+#ifdef VOLT_PROFILE
+  for (int i = 0; i < 8; ++i) tp.prof[i] = 0;
+#endif
   if (tid == 0) {
     mbar_init(c.bar, 1);
     mbar_init(c.bar + 1, 1);
+    if constexpr (TMA) {
+      for (int i = 0; i < W_RING; ++i) { mbar_init(tp.full + i, 1); mbar_init(tp.done + i, 1); }
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -113,6 +135,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   tc_fence_after();
   c.tmem = *s_tmem_p;
   const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
+  const int sq_row0 = (int)blockIdx.x * p.Tp;   // first row of this CTA's scratch square in the tensor maps
 
 #ifdef VOLT_PROFILE
   long long seg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -157,7 +180,8 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
           const int gr = r_base + row;
           TICK(0);
           bool have;
-          if constexpr (TRI) have = gemm_tc1<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
+          if constexpr (TMA) have = gemm_tma<false>(c, tp, &tmA, &tmB, sq_row0, r_base, Tp, R0, 0, R0);
+          else if constexpr (TRI) have = gemm_tc1<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           else have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           TICK(1);
           float s[32];
@@ -185,7 +209,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
               for (int q = 0; q < 8; ++q)
                 *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
               if (half_id == 0) c.tmp[row] = gen_entry(p, b, gr, gr, c.Vs, sc, dadd);   // original A_ii for the pivot test
-            } else if constexpr (TRI) {
+            } else if constexpr (PARK) {
               uint32_t u[32];   // park the rows in the accumulator columns (warp-uniform branch: rows >= 64 <=> (warp & 3) >= 2)
 #pragma unroll
               for (int q = 0; q < 32; ++q) u[q] = __float_as_uint(s[q]);
@@ -202,10 +226,13 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
             if (tid < NB && R0 + tid < T) logdet_part += logf(c.diagl[tid]);
             for (int idx = tid; idx < NB * NB; idx += NT) {
               const int r = idx >> 6, cc = idx & 63;
-              S[(size_t)(R0 + r) * ld + R0 + cc] = (cc <= r) ? c.Ct[r * CLD + cc] : 0.f;
+              // TMA instance: the diagonal block of the scratch holds the block of U = (L^-1)^T instead of L_jj (nothing reads
+              // L_jj from the scratch again; the launcher keeps callers that want L out of this instance), so that phase B's
+              // operand tiles are plain rectangles of the scratch
+              S[(size_t)(R0 + r) * ld + R0 + cc] = TMA ? LiT[r * CLD + cc] : ((cc <= r) ? c.Ct[r * CLD + cc] : 0.f);
               dinv[((size_t)j * NB + r) * NB + cc] = LiT[r * CLD + cc];
             }
-            if constexpr (TRI) __syncthreads();   // D aliases the Linv operand: every read of L_jj precedes the staging
+            if constexpr (PARK) __syncthreads();   // D aliases the Linv operand: every read of L_jj precedes the staging
             stage_linv_from_lit(c, LiT);
             if (rb) {
               const int cz = tid >> 2, part = tid & 3;
@@ -237,7 +264,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
               }
             }
             if (row >= NB) {
-              if constexpr (TRI) {
+              if constexpr (PARK) {
                 tmem_ld32(c.tmem + t_lane + (uint32_t)c0, s);
               } else {
 #pragma unroll
@@ -308,7 +335,8 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
           const int m_base = ch * CM;
           const int m = m_base + row;
           TICK(7);
-          if constexpr (TRI) gemm_tc1<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
+          if constexpr (TMA) gemm_tma<true>(c, tp, &tmA, &tmB, sq_row0, m_base, R0, R0, m_base, R0);
+          else if constexpr (TRI) gemm_tc1<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
           else gemm_tc<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
           TICK(8);
           float s[32], o[32];
@@ -427,6 +455,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   if (tid == 0 && blockIdx.x == 0 && p.z_out == nullptr && p.alpha) {
     for (int i = 0; i < 12; ++i) p.alpha[i] = (float)seg[i];
     for (int i = 0; i < 8; ++i) { p.alpha[12 + i] = (float)g_diag_prof[i]; g_diag_prof[i] = 0; }
+    if constexpr (TMA) for (int i = 0; i < 8; ++i) p.alpha[20 + i] = (float)tp.prof[i];
   }
 #endif
   tc_fence_before();
@@ -436,12 +465,42 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
 
 }  // namespace tc
 
-template <bool TRI, bool HOSTIN>
+// Tensor maps of the TMA instance: the scratch arena as a 2-D fp32 tensor (grid * Tp rows of Tp floats); boxes of
+// 16 floats x 128 rows (A operand) and 16 floats x 64 rows (B operand), SWIZZLE_64B.  Encoded on the host through the
+// driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_scratch_map(CUtensorMap* map, float* base, int Tp, long long rows, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return VOLT_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)Tp, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)Tp * sizeof(float)};
+  const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (Tp=%d rows=%lld box_rows=%d)", (int)r, Tp, rows, box_rows);
+    return VOLT_ERR_CUDA;
+  }
+  return VOLT_OK;
+}
+
+template <bool TRI, bool HOSTIN, bool TMA = false>
 static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   static size_t attr_smem_dev[16] = {};   // function attributes are per device
   size_t& attr_smem = attr_smem_dev[device_slot()];
   if (smem > attr_smem) {
-    int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel<TRI, HOSTIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    int s = check_cuda(cudaFuncSetAttribute(tc::mll_batched_tc_kernel<TRI, HOSTIN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(mll_batched_tc_kernel)");
     if (s) return s;
     attr_smem = smem;
@@ -455,14 +514,23 @@ static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   if (s) return s;
   p.scratch = reinterpret_cast<float*>(ws);
   p.dinv = p.scratch + (size_t)grid * p.Tp * p.Tp;
-  tc::mll_batched_tc_kernel<TRI, HOSTIN><<<grid, NT, smem, st>>>(p);
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  if (TMA) {
+    s = encode_scratch_map(&tmA, p.scratch, p.Tp, (long long)grid * p.Tp, 128);
+    if (s) return s;
+    s = encode_scratch_map(&tmB, p.scratch, p.Tp, (long long)grid * p.Tp, 64);
+    if (s) return s;
+  }
+  tc::mll_batched_tc_kernel<TRI, HOSTIN, TMA><<<grid, NT, smem, st>>>(p, tmA, tmB);
   return check_cuda(cudaGetLastError(), "mll_batched_tc_kernel");
 }
 
 // resident CTAs (= series in flight) of the batched kernel for series of length T: the first wave of a batch
 int mll_tc_resident_ctas(int T, int two_rhs) {
   const int Tp = (T + NB - 1) / NB * NB;
-  const size_t vec = sizeof(float) * (size_t)((two_rhs ? 4 : 3) * Tp + NB + 2 * NB + 32 + 12);
+  const size_t vec = sizeof(float) * (size_t)((two_rhs ? 4 : 3) * Tp + NB + 2 * NB + 32 + 12 + 20);
   const size_t smem3 = tc::Y_VEC_OFF + vec;
   if (3 * (smem3 + 1024) <= 233472) return 3 * sm_count();
   const size_t smem = tc::VEC_OFF + vec;
@@ -470,10 +538,19 @@ int mll_tc_resident_ctas(int T, int two_rhs) {
   return sm_count() * (per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm));
 }
 
+// Default choice between the register-staged instances and the TMA-fed one, from measurements on the B200.
+// B200, one launch (ms): 256 x T=1024: 2.41 TMA vs 2.87 register-staged; 296 x 512: 0.538 vs 0.551; 148 x 512: 0.430 both;
+// 444 x 512: 0.906 vs 0.776 and 1024 x 512: 1.86 vs 1.82 for the three-CTA register-staged instance, which keeps those.
+static bool use_tma_default(int B, int T, int sms) {
+  const int Tp = (T + NB - 1) / NB * NB;
+  if (Tp > 832) return true;                        // no three-CTA instance at this length
+  return B > sms && B <= 2 * sms;                   // two series per SM: the two-CTA instances, TMA-fed
+}
+
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.Tp = (p.T + NB - 1) / NB * NB;
   p.nb = p.Tp / NB;
-  const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12);
+  const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12 + 20);
   const size_t smem_total = 233472, smem_cta_reserved = 1024;   // sm_100: 228 KB per SM, 1 KB reserved per resident CTA
   // three resident CTAs per SM when the small shared-memory map fits three times (T <= 832); VOLT_TC_CTAS=2 / 3 forces the
   // double-buffered two-CTA / the three-CTA kernel (A/B timing)
@@ -486,9 +563,22 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   // overlapped (0.757 ms for 444 series vs 0.937).  So: batches of at most two series per SM, and batches whose last
   // wave would be a single straggler per SM (3 < B / SMs <= 4), take the two-CTA instance.
   const int sms = sm_count();
+  {
+    static const int tma_first = [] { const char* e = getenv("VOLT_TC_TMA"); return e ? atoi(e) : -1; }();
+    const size_t smem_w0 = tc::W_VEC_OFF + vec;
+    if (tma_first == 2 && !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total)
+      return launch_tc<false, false, true>(p, st, smem_w0, 2);   // VOLT_TC_TMA=2: force the TMA instance (A/B timing)
+  }
   const bool prefer2 = forced != 3 && ((p.B <= 2 * sms) || (p.B > 3 * sms && p.B <= 4 * sms));
   if (!force2 && !prefer2 && 3 * (smem3 + smem_cta_reserved) <= smem_total)
     return hostin ? launch_tc<true, true>(p, st, smem3, 3) : launch_tc<true, false>(p, st, smem3, 3);
+  // TMA-fed instance (operand tiles through cp.async.bulk.tensor, two CTAs per SM): device-pointer entry, callers that do
+  // not ask for the factor itself (its scratch keeps the inverse blocks on the diagonal).  VOLT_TC_TMA=0 disables it.
+  static const int tma_env = [] { const char* e = getenv("VOLT_TC_TMA"); return e ? atoi(e) : -1; }();
+  const size_t smem_w = tc::W_VEC_OFF + vec;
+  const bool tma_ok = !hostin && !p.L_out && 2 * (smem_w + smem_cta_reserved) <= smem_total;
+  const bool want_tma = tma_env == 2 || (tma_env != 0 && use_tma_default(p.B, p.T, sms));
+  if (tma_ok && want_tma && (forced != 2 || tma_env == 2)) return launch_tc<false, false, true>(p, st, smem_w, 2);
   const size_t smem = tc::VEC_OFF + vec;
   if (smem > 227 * 1024) {
     set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);

@@ -45,6 +45,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of a fully converged warp.  The MMA / TMA issue sections run as `if (warp_uniform == k) { if (elect_one()) ... }`
+// with operands derived from warp-uniform values: ptxas then keeps descriptors and addresses in uniform registers and emits
+// one UTCHMMA per tcgen05.mma.  Issued from a thread-divergent branch (`if (tid == 0)`) every operand sits in a vector
+// register and each instruction is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" loop -- measured: ~95 cycles
+// of issue time per MMA, i.e. the issuing thread, not the tensor pipe, paced the GEMM loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t make_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
@@ -168,6 +180,8 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
   const int row = 32 * (w & 3) + lane, half_id = w >> 2;
   const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
   uint8_t* RAW = c.X;                                   // 16 KB raw A tile, rows of 128 B, 16-byte chunks XOR-swizzled
+  const int wu = uniform_warp_id();                     // MMA issue from one elected lane of warp 0, uniform operands (elect_one)
+  const uint32_t tmem_u = make_uniform(c.tmem), xb = s_u32(c.X);
   float4 ra[4], rb[2];
   auto gload = [&](int k0) {
 #pragma unroll
@@ -219,18 +233,21 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (wu == 0) {
       tc_fence_after();
-      const uint64_t dbh = make_desc(s_u32(BH)), dbl = make_desc(s_u32(BL));
+      if (elect_one()) {
+        const uint64_t dbh = make_desc(xb + X_B0 + h * (2 * B_TILE)), dbl = make_desc(xb + X_B0 + h * (2 * B_TILE) + B_TILE);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t adv = (uint64_t)(2 * ks);
-        const uint32_t ah = c.tmem + TM_PHI + 32 * h + 8 * ks, al = c.tmem + TM_PLO + 32 * h + 8 * ks;
-        umma_tf32_ts(c.tmem + TM_ACC0, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
-        umma_tf32_ts(c.tmem + TM_ACC0, ah, dbl + adv, 1u);
-        umma_tf32_ts(c.tmem + TM_ACC0, ah, dbh + adv, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adv = (uint64_t)(2 * ks);
+          const uint32_t ah = tmem_u + TM_PHI + 32 * h + 8 * ks, al = tmem_u + TM_PLO + 32 * h + 8 * ks;
+          umma_tf32_ts(tmem_u + TM_ACC0, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32_ts(tmem_u + TM_ACC0, ah, dbl + adv, 1u);
+          umma_tf32_ts(tmem_u + TM_ACC0, ah, dbh + adv, 1u);
+        }
+        umma_commit(c.bar + h);
       }
-      umma_commit(c.bar + h);
+      __syncwarp();
     }
   }
   wait_mma2(c, (nk - 1) & 1);
@@ -259,20 +276,24 @@ static __device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (uniform_warp_id() == 0) {
     tc_fence_after();
-    const uint32_t lb = s_u32(c.Lr);
+    const uint32_t tmem_u = make_uniform(c.tmem);
+    if (elect_one()) {
+      const uint32_t lb = s_u32(c.Lr);
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const int kt = ks >> 2;
-      const uint64_t adv = (uint64_t)(2 * (ks & 3));
-      const uint64_t dbh = make_desc(lb + kt * B_TILE) + adv, dbl = make_desc(lb + (2 + kt) * B_TILE) + adv;
-      const uint32_t ah = c.tmem + TM_PHI + 8 * ks, al = c.tmem + TM_PLO + 8 * ks;
-      umma_tf32_ts(c.tmem + TM_ACC1, al, dbh, ks == 0 ? 0u : 1u);
-      umma_tf32_ts(c.tmem + TM_ACC1, ah, dbl, 1u);
-      umma_tf32_ts(c.tmem + TM_ACC1, ah, dbh, 1u);
+      for (int ks = 0; ks < 8; ++ks) {
+        const int kt = ks >> 2;
+        const uint64_t adv = (uint64_t)(2 * (ks & 3));
+        const uint64_t dbh = make_desc(lb + kt * B_TILE) + adv, dbl = make_desc(lb + (2 + kt) * B_TILE) + adv;
+        const uint32_t ah = tmem_u + TM_PHI + 8 * ks, al = tmem_u + TM_PLO + 8 * ks;
+        umma_tf32_ts(tmem_u + TM_ACC1, al, dbh, ks == 0 ? 0u : 1u);
+        umma_tf32_ts(tmem_u + TM_ACC1, ah, dbl, 1u);
+        umma_tf32_ts(tmem_u + TM_ACC1, ah, dbh, 1u);
+      }
+      umma_commit(c.bar);
     }
-    umma_commit(c.bar);
+    __syncwarp();
   }
   wait_mma(c);
   tc_fence_after();
@@ -307,6 +328,8 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
   uint8_t* RAW = c.X;
   uint8_t* BH = c.X + Y_BH;
   uint8_t* BL = c.X + Y_BL;
+  const int wu = uniform_warp_id();                     // MMA issue from one elected lane of warp 0, uniform operands (elect_one)
+  const uint32_t tmem_u = make_uniform(c.tmem), xb = s_u32(c.X);
   float4 ra[4], rb[2];
   auto gload_b = [&](int k0) {
 #pragma unroll
@@ -361,18 +384,21 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (wu == 0) {
       tc_fence_after();
-      const uint64_t dbh = make_desc(s_u32(BH)), dbl = make_desc(s_u32(BL));
+      if (elect_one()) {
+        const uint64_t dbh = make_desc(xb + Y_BH), dbl = make_desc(xb + Y_BL);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t adv = (uint64_t)(2 * ks);
-        const uint32_t ah = c.tmem + T3_HI + 8 * ks, al = c.tmem + T3_LO + 8 * ks;
-        umma_tf32_ts(c.tmem + T3_ACC, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
-        umma_tf32_ts(c.tmem + T3_ACC, ah, dbl + adv, 1u);
-        umma_tf32_ts(c.tmem + T3_ACC, ah, dbh + adv, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adv = (uint64_t)(2 * ks);
+          const uint32_t ah = tmem_u + T3_HI + 8 * ks, al = tmem_u + T3_LO + 8 * ks;
+          umma_tf32_ts(tmem_u + T3_ACC, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32_ts(tmem_u + T3_ACC, ah, dbl + adv, 1u);
+          umma_tf32_ts(tmem_u + T3_ACC, ah, dbh + adv, 1u);
+        }
+        umma_commit(c.bar);
       }
-      umma_commit(c.bar);
+      __syncwarp();
     }
   }
   wait_mma(c);
@@ -386,6 +412,8 @@ static __device__ void trsm_tc1(Ctx& c, const float (&s)[32], float (&o)[32], in
   const int tid = threadIdx.x, w = tid >> 5;
   const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
   const uint32_t lb = s_u32(c.Lr);
+  const int wu = uniform_warp_id();
+  const uint32_t tmem_u = make_uniform(c.tmem);
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     if (half_id == pass) {
@@ -401,18 +429,21 @@ static __device__ void trsm_tc1(Ctx& c, const float (&s)[32], float (&o)[32], in
     }
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (wu == 0) {
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t adv = (uint64_t)(2 * ks);
-        const uint64_t dbh = make_desc(lb + pass * B_TILE) + adv, dbl = make_desc(lb + (2 + pass) * B_TILE) + adv;
-        const uint32_t ah = c.tmem + T3_HI + 8 * ks, al = c.tmem + T3_LO + 8 * ks;
-        umma_tf32_ts(c.tmem + T3_ACC, al, dbh, (pass == 0 && ks == 0) ? 0u : 1u);
-        umma_tf32_ts(c.tmem + T3_ACC, ah, dbl, 1u);
-        umma_tf32_ts(c.tmem + T3_ACC, ah, dbh, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adv = (uint64_t)(2 * ks);
+          const uint64_t dbh = make_desc(lb + pass * B_TILE) + adv, dbl = make_desc(lb + (2 + pass) * B_TILE) + adv;
+          const uint32_t ah = tmem_u + T3_HI + 8 * ks, al = tmem_u + T3_LO + 8 * ks;
+          umma_tf32_ts(tmem_u + T3_ACC, al, dbh, (pass == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32_ts(tmem_u + T3_ACC, ah, dbl, 1u);
+          umma_tf32_ts(tmem_u + T3_ACC, ah, dbh, 1u);
+        }
+        umma_commit(c.bar);
       }
-      umma_commit(c.bar);
+      __syncwarp();
     }
     wait_mma(c);
     tc_fence_after();
@@ -458,6 +489,192 @@ __device__ __forceinline__ void stage_linv_from_dinv(Ctx& c, const float* D) {
     const int kt = kc >> 3;
     st_split(c.Lr + kt * B_TILE, c.Lr + (2 + kt) * B_TILE, n, kc & 7, v);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed GEMM loop (the "W" instance of the batched kernel: two CTAs per SM, 256 TMEM columns).
+//
+// The register-staged loops above spend ~200 instructions per thread and k-tile on moving operands (LDG, address and
+// bounds arithmetic, STS of the raw tile, a barrier, LDS, split, tcgen05.st): the loop is bound by instruction issue, not by
+// the tensor pipe.  Here the raw fp32 operand tiles are brought in by the TMA unit (cp.async.bulk.tensor.2d, one
+// elected thread, completion on an mbarrier) into a ring of shared-memory slots, 16 floats of K at a time:
+//     slot s:  A raw 128 rows x 64 B | B raw 64 rows x 64 B      (SWIZZLE_64B, the layout the tensor map writes and the
+//                                                                  UMMA descriptor reads)
+// The B tile is used in place as the "hi" MMA operand (the tensor core ignores the low 13 mantissa bits of a raw fp32
+// operand); threads only compute the "lo" tiles: every thread reads 32 bytes of its accumulator row of A, splits them and
+// writes hi / lo to tensor memory (TS-form MMA, as above), and one 16-byte chunk of B, whose lo part goes to a second
+// shared tile.  TMA of k-tile g + RING - 1 is issued as soon as the MMAs of k-tile g - 1 have released its slot, so up to
+// RING - 1 tiles are in flight while one is being consumed.  Per k-tile and thread: 3 LDS.128, 1 STS.128, 24 ALU,
+// 2 tcgen05.st, 1 barrier.
+constexpr int W_RING = 4;
+constexpr uint32_t HA_TILE = 128u * 64u, HB_TILE = 64u * 64u;      // bytes: 128 x 16 floats, 64 x 16 floats
+constexpr uint32_t W_SLOT = HA_TILE + HB_TILE;                     // 12 KB
+constexpr uint32_t W_BL = W_RING * W_SLOT;                         // two B lo tiles after the ring
+constexpr int W_BLN = 3;                                           // B lo tiles / TMEM A stages cycle with period 3 (see gemm_tma)
+constexpr uint32_t W_BYTES = W_BL + W_BLN * HB_TILE;               // 60 KB; aliased by LiT | diag scratch and the store tiles
+constexpr uint32_t W_L_OFF = W_BYTES, W_CT_OFF = W_L_OFF, W_VEC_OFF = W_L_OFF + L_BYTES;   // D aliases the Linv operand
+static_assert(X_TMP + DIAG2_SCRATCH_FLOATS * 4 <= W_BYTES && 8 * 1152 * 4 <= W_BYTES, "diag scratch / store tiles must fit the ring region");
+
+struct TmaPipe {
+  uint64_t* full;    // [W_RING] TMA landed
+  uint64_t* done;    // [W_RING] MMAs of the tile that used the slot have completed
+  uint32_t g;        // running k-tile counter of this CTA (slot = g % W_RING, use = g / W_RING)
+#ifdef VOLT_PROFILE
+  long long prof[8];
+#endif
+};
+
+// K-major SWIZZLE_64B operand descriptor: rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t swz64(int row, int chunk) { return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(s_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// acc0 = A[a_row0 + r, k_lo:k_hi] . B[b_row0 + n, k_lo:k_hi]^T (r < 128, n < 64), both operands rows of this CTA's scratch
+// square (tensor-map row = sq_row0 + local row).  PHASE_B: A = U = X^T, whose entries below the block diagonal are zero (the
+// scratch holds L there) -- masked when the tile is split; its diagonal blocks were copied into the scratch beforehand.
+#ifdef VOLT_PROFILE
+static __device__ long long g_tma_prof[8];
+#define WTICK(i) do { if (threadIdx.x == 0) { const long long _n = clock64(); tp.prof[i] += _n - wlast; wlast = _n; } } while (0)
+#else
+#define WTICK(i) do { } while (0)
+#endif
+template <bool PHASE_B>
+__device__ bool gemm_tma(Ctx& c, TmaPipe& tp, const void* tmA, const void* tmB, int sq_row0, int a_row0, int a_row_end, int b_row0, int k_lo,
+                         int k_hi) {
+  const int nk = (k_hi - k_lo) / 16;
+  if (nk <= 0) return false;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int row = 32 * (w & 3) + lane, half_id = w >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  const uint32_t xb = s_u32(c.X);
+  // writes of earlier phases (panel stores, diagonal blocks) must be visible to the async proxy before any TMA reads them,
+  // and the ring region may have been used as scratch by the epilogue
+#ifdef VOLT_PROFILE
+  long long wlast = clock64();
+#endif
+  fence_proxy_async_all();
+  __syncthreads();
+  WTICK(0);
+  const uint32_t g0 = tp.g;
+  // Two elected lanes in different warps share the asynchronous work of a k-tile: one lane of warp 0 issues the MMAs, one
+  // lane of warp 4 waits for the slot of the tile RING - 1 ahead to be released and issues its TMA.  Nobody else waits for MMA
+  // completions inside the loop: TMEM stage / B lo tile g % 3 was last read by the MMAs of tile g - 3, whose completion
+  // thread 128 observed (wait on done[g - 3], issued in iteration g - 2) before the barrier of tile g - 1 -- which every
+  // thread passes before it writes stage g % 3 again.
+  auto issue_tma = [&](int kt) {       // one elected thread
+    const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
+    mbar_expect_tx(tp.full + s, W_SLOT);
+    tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, k_lo + 16 * kt, sq_row0 + a_row0);
+    tma_load_2d(tmB, xb + s * W_SLOT + HA_TILE, tp.full + s, k_lo + 16 * kt, sq_row0 + b_row0);
+  };
+  const int wu = uniform_warp_id();
+  const uint32_t tmem_u = make_uniform(c.tmem);
+  if (wu == 4) {
+    if (elect_one()) {
+      const int pre = nk < W_RING - 1 ? nk : W_RING - 1;
+      for (int kt = 0; kt < pre; ++kt) issue_tma(kt);
+    }
+    __syncwarp();
+  }
+  const bool row_ok = (a_row0 + row) < a_row_end;
+  const int mb = (a_row0 + row) >> 6;
+  for (int kt = 0; kt < nk; ++kt) {
+    const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING, ts = g % W_BLN;
+    const uint8_t* RAW = c.X + s * W_SLOT;
+    const uint8_t* BH = RAW + HA_TILE;
+    uint8_t* BL = c.X + W_BL + ts * HB_TILE;
+    WTICK(1);
+    mbar_wait(tp.full + s, (g / W_RING) & 1u);
+    WTICK(2);
+    {
+      uint32_t hi[8], lo[8];
+      const bool live = row_ok && !(PHASE_B && ((k_lo + 16 * kt) >> 6) < mb);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(RAW + swz64(row, 2 * half_id + q));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t u = live ? __float_as_uint(e[j]) : 0u;
+          hi[4 * q + j] = u;
+          lo[4 * q + j] = __float_as_uint(__uint_as_float(u) - __uint_as_float(u & 0xffffe000u));
+        }
+      }
+      tmem_st8(c.tmem + lane_base + TM_PHI + (uint32_t)(16 * ts + 8 * half_id), hi);
+      tmem_st8(c.tmem + lane_base + TM_PLO + (uint32_t)(16 * ts + 8 * half_id), lo);
+      const uint32_t off = swz64(tid >> 2, tid & 3);
+      const float4 b = *reinterpret_cast<const float4*>(BH + off);
+      float4 l;
+      l.x = b.x - __uint_as_float(__float_as_uint(b.x) & 0xffffe000u);
+      l.y = b.y - __uint_as_float(__float_as_uint(b.y) & 0xffffe000u);
+      l.z = b.z - __uint_as_float(__float_as_uint(b.z) & 0xffffe000u);
+      l.w = b.w - __uint_as_float(__float_as_uint(b.w) & 0xffffe000u);
+      *reinterpret_cast<float4*>(BL + off) = l;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    WTICK(4);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    WTICK(5);
+    if (wu == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dbh = make_desc64(xb + s * W_SLOT + HA_TILE), dbl = make_desc64(xb + W_BL + ts * HB_TILE);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t adv = (uint64_t)(2 * ks);
+          const uint32_t ah = tmem_u + TM_PHI + 16 * ts + 8 * ks, al = tmem_u + TM_PLO + 16 * ts + 8 * ks;
+          umma_tf32_ts(tmem_u + TM_ACC0, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32_ts(tmem_u + TM_ACC0, ah, dbl + adv, 1u);
+          umma_tf32_ts(tmem_u + TM_ACC0, ah, dbh + adv, 1u);
+        }
+        umma_commit(tp.done + s);
+      }
+      __syncwarp();
+    } else if (wu == 4) {
+      // refill: k-tile kt + RING - 1 goes into the slot k-tile kt - 1 used; its MMAs were issued a whole tile ago
+      // (the wait is unconditional: it is also what makes the reuse of TMEM stage / B lo tile (g + 2) % 3 safe, see above)
+      if (elect_one()) {
+        if (kt >= 1) mbar_wait(tp.done + ((g - 1) % W_RING), ((g - 1) / W_RING) & 1u);
+        if (kt + W_RING - 1 < nk) issue_tma(kt + W_RING - 1);
+      }
+      __syncwarp();
+    }
+  }
+  WTICK(1);
+  tp.g = g0 + (uint32_t)nk;
+  // drain: the last commit covers every MMA issued before it
+  {
+    const uint32_t gl = g0 + (uint32_t)nk - 1u;
+    mbar_wait(tp.done + (gl % W_RING), (gl / W_RING) & 1u);
+  }
+  WTICK(6);
+  tc_fence_after();
+  return true;
 }
 
 // A-generator for one accumulator row: s[q] <- A[gr][gc0 + q] - s[q], q = 0..31.  Fast path (no identity padding, on-the-fly

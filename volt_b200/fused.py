@@ -1,8 +1,9 @@
 """Device-resident Adam loops for the two training loops on the hot path.
 
 `TrainVoltMagpieModel` with a moving-average mean trains ONE scalar (the likelihood raw_noise, train_utils.py:201-203)
-against a fixed covariance and a fixed residual; `TrainVolModel` trains (raw_noise, raw_vol) of the BM vol model.
-Both are `train_iters` repetitions of [transform parameters -> exact MLL + analytic gradient (one launch of the fused
+against a fixed covariance and a fixed residual; `TrainVolModel` trains (raw_noise, raw_vol) of the BM vol model;
+`TrainDataModel` and the constant / linear / loglinear branches of `TrainVoltMagpieModel` train raw_noise plus the
+parameters of the mean (train_utils.py:98-144, 201-227).  All are `train_iters` repetitions of [transform parameters -> exact MLL + analytic gradient (one launch of the fused
 CUDA kernel) -> Adam update].  Here one iteration is captured in a CUDA graph and replayed: no per-iteration host
 synchronisation, H2D/D2H traffic or Python-side autograd.  The arithmetic is the reference's: GPyTorch's parameter
 transforms, MLL / T, torch.optim.Adam defaults (betas 0.9 / 0.999, eps 1e-8, no weight decay, bias correction).
@@ -11,7 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib, ops
-from ._lib import S_ALAL, S_ALR, S_DNOISE, S_MLL, S_TRINV, VOLT_NSCALARS
+from ._lib import S_ALAL, S_ALR, S_DNOISE, S_DRAW, S_MLL, S_TRINV, VOLT_NSCALARS
 from .means import _MAMean
 
 _B1, _B2, _EPS = 0.9, 0.999, 1e-8
@@ -117,6 +118,84 @@ def _fit_noise_ma(model, likelihood, train_x, target, lr, train_iters, printing)
     return True
 
 
+def _fit_parametric_mean(model, likelihood, train_x, target, lr, train_iters, printing):
+    """TrainDataModel (train_utils.py:98-144) and the constant / linear / loglinear branches of TrainVoltMagpieModel
+    (:201-227): the trained tensors are raw_noise and the mean's parameters (ConstantMean: constant; LinearMean /
+    LogLinearMean: weights, bias -- means/loglinear_mean.py:5-21).  Per iteration: evaluate the mean (elementwise, T
+    values), one launch of the fused-step kernel (MLL, dMLL/draw_noise, alpha), the mean gradients as alpha-weighted sums
+    (dMLL/dm = alpha / T, so d(-MLL)/dtheta = -(alpha / T) . dm/dtheta), one Adam update -- all on the device, captured
+    once in a CUDA graph and replayed."""
+    from . import gp
+    from .means import LogLinearMean
+
+    mm = model.mean_module
+    dev = ops._dev()
+    lib = _lib.load()
+    spec = model.train_cov.fused()
+    if spec is None or spec[0] != "vol":
+        return False
+    _, x, vol = spec
+    T = target.shape[-1]
+    xd = ops._f32(x, dev).reshape(-1)
+    tx = ops._f32(train_x, dev).reshape(-1)
+    vd = ops._f32(vol, dev).reshape(1, T)
+    yd = ops._f32(target, dev).reshape(T)
+    raw = ops._f32(likelihood.raw_noise, dev).reshape(1).clone()
+    if isinstance(mm, gp.ConstantMean):
+        kind, names = "constant", ["constant"]
+    elif isinstance(mm, LogLinearMean):
+        kind, names = "loglinear", ["weights", "bias"]
+    else:
+        kind, names = "linear", ["weights", "bias"]
+    params = [ops._f32(getattr(mm, n), dev).reshape(1).clone() for n in names]
+    opt = _Adam([raw] + params, lr)      # registration order: likelihood first (ExactGP), then mean_module
+    resid = torch.empty(1, T, device=dev)
+    scal = torch.empty(1, VOLT_NSCALARS, device=dev)
+    alpha = torch.empty(1, T, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    loss = torch.empty(1, device=dev)
+    inv_T = 1.0 / T
+
+    def iteration():
+        if kind == "constant":
+            torch.sub(yd, params[0], out=resid[0])
+            dm = None
+        else:
+            lin = tx * params[0] + params[1]                       # x @ weights + bias
+            if kind == "loglinear":
+                inside = lin > 1e-6                                # clamp(min=1e-6): zero gradient below the clamp
+                lin_c = lin.clamp(min=1e-6)
+                torch.sub(yd, lin_c.log(), out=resid[0])
+                dm = inside.to(lin.dtype) / lin_c                  # d log(clamp(.)) / d lin
+            else:
+                torch.sub(yd, lin, out=resid[0])
+                dm = None
+        _lib.check(lib.volt_mll_grad_vol_raw(xd.data_ptr(), 0, vd.data_ptr(), ops.VOL_SIGMA, resid.data_ptr(), raw.data_ptr(), 0, 1, T,
+                                             1e-6, 3, scal.data_ptr(), alpha.data_ptr(), info.data_ptr(), loss.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "volt_mll_grad_vol_raw")
+        bad.add_(info.ne(0).to(torch.int32))
+        g_m = alpha[0] * (-inv_T)                                  # d(-MLL) / d mean
+        if dm is not None:
+            g_m = g_m * dm
+        grads = [-scal[0, S_DRAW].reshape(1)]
+        if kind == "constant":
+            grads.append(g_m.sum().reshape(1))
+        else:
+            grads += [(g_m * tx).sum().reshape(1), g_m.sum().reshape(1)]
+        opt.step(grads)
+
+    _run(iteration, train_iters, printing, scal, capturable=T < LARGE_PATH_T)
+    if int(bad) != 0:
+        raise ops.NotPSDError("training: covariance not positive definite after jitter retries")
+    with torch.no_grad():
+        likelihood.raw_noise.data = raw.to(likelihood.raw_noise.device).reshape(likelihood.raw_noise.shape)
+        for n, v in zip(names, params):
+            t = getattr(mm, n)
+            t.data = v.to(t.device).reshape(t.shape)
+    return True
+
+
 def _fit_bmgp(model, likelihood, train_x, target, lr, train_iters, printing):
     dev = ops._dev()
     lib = _lib.load()
@@ -163,6 +242,8 @@ def _fit_bmgp(model, likelihood, train_x, target, lr, train_iters, printing):
 
 def try_fused_loop(model, likelihood, train_x, target, lr, train_iters, printing):
     """Returns True when the loop was run on the device-resident path, False when the caller must use the generic one."""
+    from . import gp
+    from .means import LogLinearMean
     from .models import BMGP, _VoltBase
 
     trainable = [n for n, p in model.named_parameters() if p.requires_grad]
@@ -172,4 +253,9 @@ def try_fused_loop(model, likelihood, train_x, target, lr, train_iters, printing
     if isinstance(model, BMGP) and target.ndim == 1 and model.likelihood is likelihood \
             and trainable == ["likelihood.noise_covar.raw_noise", "covar_module.raw_vol"]:
         return _fit_bmgp(model, likelihood, train_x, target, lr, train_iters, printing)
+    if isinstance(model, _VoltBase) and target.ndim == 1 and model.likelihood is likelihood and train_x.ndim == 1 \
+            and type(model.mean_module) in (gp.ConstantMean, gp.LinearMean, LogLinearMean):
+        mean_names = ["mean_module." + n for n, _ in model.mean_module.named_parameters()]
+        if trainable == ["likelihood.noise_covar.raw_noise"] + mean_names and all(p.numel() == 1 for p in model.mean_module.parameters()):
+            return _fit_parametric_mean(model, likelihood, train_x, target, lr, train_iters, printing)
     return False
