@@ -13,6 +13,26 @@ constexpr int BS_LD = NB + 4;
 constexpr int CT_LD = CM + 4;  // Ct[c][r]: chunk result, column-major ("transposed") so it can be re-used as a K-major A tile
 constexpr int LI_LD = NB + 4;  // LiT[k][c] = Linv[c][k]
 
+// CTA barrier of the NT = 256 worker threads: named barrier 1 with an explicit thread count.  Identical to wsync() in
+// a 256-thread CTA; in the batched kernel's instance that adds two control warps (TMA producer / MMA issuer, chol_tc.cu)
+// those warps never take part in the workers' barriers.
+__device__ __forceinline__ void wsync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// block_sum (common.cuh) over the 256 worker threads
+__device__ __forceinline__ float block_sum_w(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  wsync();
+  if (lane == 0) red[w] = v;
+  wsync();
+  float r = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  wsync();
+  r = red[0];
+  wsync();
+  return r;
+}
+
 struct Smem {
   float* As; float* Bs; float* Ct; float* LiT; float* Vs; float* z; float* al; float* z2;
   float* diagl; float* tmp; float* red; int* flag;
@@ -79,13 +99,13 @@ __device__ void gemm_tn(float (&acc)[8][4], const float* S, int ld, int a_row0, 
   };
   gload(k_lo);
   sstore(0);
-  __syncthreads();
+  wsync();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) gload(k_lo + (kt + 1) * BK);
     mma_tile(acc, As + buf * (BK * AS_LD), AS_LD, Bs + buf * (BK * BS_LD), BS_LD, BK, ty, tx);
     if (kt + 1 < nk) sstore(buf ^ 1);
-    __syncthreads();
+    wsync();
   }
 }
 
@@ -97,7 +117,7 @@ __device__ void potrf64(float* Ct, float* diagl, int* flag, int col0) {
   const int tid = threadIdx.x;
   const int r = tid & 63, kg = tid >> 6;
   for (int c = 0; c < NB; ++c) {
-    __syncthreads();
+    wsync();
     const float d = Ct[c * CLD + c];
     if (!(d > 0.f)) {
       if (tid == 0 && *flag < 0) *flag = col0 + c;
@@ -106,14 +126,14 @@ __device__ void potrf64(float* Ct, float* diagl, int* flag, int col0) {
     const float inv = 1.f / l;
     if (tid == c) diagl[c] = l;
     if (tid < NB && tid > c) Ct[c * CLD + tid] *= inv;
-    __syncthreads();
+    wsync();
     const float lr = Ct[c * CLD + r];
     for (int k = c + 1 + kg; k < NB; k += 4)
       if (r >= k) Ct[k * CLD + r] = fmaf(-lr, Ct[c * CLD + k], Ct[k * CLD + r]);
   }
-  __syncthreads();
+  wsync();
   if (tid < NB) Ct[tid * CLD + tid] = diagl[tid];
-  __syncthreads();
+  wsync();
 }
 
 // LiT[k][c] = Linv[c][k], Linv = L^-1 for the 64x64 lower-triangular L in Ct, by recursive doubling:
@@ -122,9 +142,9 @@ template <int CLD>
 __device__ void trtri64(const float* Ct, float* LiT, float* tmpbuf) {
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NB * LI_LD; idx += NT) LiT[idx] = 0.f;
-  __syncthreads();
+  wsync();
   if (tid < NB) LiT[tid * LI_LD + tid] = 1.f / Ct[tid * CLD + tid];
-  __syncthreads();
+  wsync();
   for (int s = 1; s < NB; s <<= 1) {
     // step 1: Tm[r][c] = sum_k L_CA[r][k] Linv_AA[k][c], r,c in [0,s) per pair, k >= c
     for (int o = tid; o < 32 * s; o += NT) {
@@ -134,7 +154,7 @@ __device__ void trtri64(const float* Ct, float* LiT, float* tmpbuf) {
       for (int k = cc; k < s; ++k) acc = fmaf(Ct[(a0 + k) * CLD + c0 + rr], LiT[(a0 + cc) * LI_LD + a0 + k], acc);
       tmpbuf[(c0 + rr) * NB + a0 + cc] = acc;
     }
-    __syncthreads();
+    wsync();
     // step 2: Linv_CA[r][c] = - sum_k Linv_CC[r][k] Tm[k][c], k <= r
     for (int o = tid; o < 32 * s; o += NT) {
       const int pair = o / (s * s), rc = o % (s * s), rr = rc / s, cc = rc % s;
@@ -143,7 +163,7 @@ __device__ void trtri64(const float* Ct, float* LiT, float* tmpbuf) {
       for (int k = 0; k <= rr; ++k) acc = fmaf(LiT[(c0 + k) * LI_LD + c0 + rr], tmpbuf[(c0 + k) * NB + a0 + cc], acc);
       LiT[(a0 + cc) * LI_LD + c0 + rr] = -acc;
     }
-    __syncthreads();
+    wsync();
   }
 }
 
@@ -287,7 +307,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
       }
     }
     DTICK(0);
-    __syncthreads();
+    wsync();
     DTICK(1);
     if (R > 0) {
       // ---- P2: panel solve X = S_panel Linv16^T, 16-row groups x (2 x 2 tiles); result kept transposed in XT
@@ -300,7 +320,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
         XT[tj * XT_LD + r0] = x00; XT[(tj + 8) * XT_LD + r0] = x01;
         XT[tj * XT_LD + r0 + 8] = x10; XT[(tj + 8) * XT_LD + r0 + 8] = x11;
       }
-      __syncthreads();
+      wsync();
       DTICK(2);
       // ---- P3: write the panel back (row fastest) and apply the trailing update D[r][c] -= X[r].X[c] in 4 x 4 tiles
       //      that touch the lower triangle (the strictly-upper entries a diagonal tile also updates are never read)
@@ -336,7 +356,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
           *dst = v;
         }
       }
-      __syncthreads();
+      wsync();
       DTICK(3);
     }
   }
@@ -355,7 +375,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
       float* wt = WT + (tg * 16 + tj) * 20 + ti;
       wt[0] = w00; wt[8 * 20] = w01; wt[8] = w10; wt[8 * 20 + 8] = w11;
     }
-    __syncthreads();
+    wsync();
     if (tid < nblk * 64) {
       const float* a0 = I16 + pb * 16 * I16_LD + ti * I16_LD;
       const float* b0 = WT + (tg * 16 + tj) * 20;
@@ -364,7 +384,7 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
       float* lt = LiT + (16 * qb + tj) * RLD + 16 * pb + ti;
       lt[0] = -l00; lt[8 * RLD] = -l01; lt[8] = -l10; lt[8 * RLD + 8] = -l11;
     }
-    __syncthreads();
+    wsync();
   }
   DTICK(4);
 }

@@ -59,9 +59,9 @@ static __device__ __noinline__ bool hostin_prologue(const int* ready, int* ready
       if (f == 0) *ready_timeout = 1;
       *sflag = f;
     }
-    __syncthreads();
+    wsync();
     const int arrived = *sflag;
-    __syncthreads();
+    wsync();
     if (arrived == 0) return false;
   }
   if (tid < 32) cumtrapz_warp(xs, vs, T, mode, 1, Vs, tid);
@@ -71,11 +71,53 @@ static __device__ __noinline__ bool hostin_prologue(const int* ready, int* ready
 
 // TMA = true: the "W" instance (two CTAs per SM): operand tiles of every GEMM loop arrive through the TMA unit (gemm_tma,
 // chol_tc_dev.cuh); shared-memory map and accumulator parking as in the three-CTA instance, 256 TMEM columns, one-pass TRSM.
-template <bool TRI, bool HOSTIN = false, bool TMA = false>
-__global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllParams p, const __grid_constant__ CUtensorMap tmA,
-                                                                         const __grid_constant__ CUtensorMap tmB) {
-  static_assert(!(TRI && TMA), "the TMA instance is a two-CTA instance");
-  constexpr bool PARK = TRI || TMA;   // chunk-0 panel rows wait in the accumulator columns during the diagonal factorisation
+// TMA = 2: the same with two control warps (warp 8: MMA issuer, warp 9: TMA producer; gemm_w2_worker / w2_control): 320 threads.
+constexpr int W2_THREADS = NT + 64;
+
+// Control warps of the TMA = 2 instance: they walk the same deterministic schedule of GEMM calls as the workers (series loop,
+// psd_safe_cholesky attempts, phase A block steps x row chunks, phase B) and feed / issue every k-tile of every call.
+__device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtensorMap* tmA, const CUtensorMap* tmB, int wu) {
+  const int Tp = p.Tp, nb = p.nb;
+  const uint32_t xb = s_u32(c.X), tmem_u = make_uniform(c.tmem);
+  const int sq_row0 = (int)blockIdx.x * Tp;
+  const bool is_tma = (wu == 9);
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    for (int attempt = 0;; ++attempt) {
+      for (int j = 1; j < nb; ++j) {                       // block step 0 has no earlier columns: no GEMM call
+        const int R0 = j * NB, nk = R0 / 16;
+        const int nch = (Tp - R0 + CM - 1) / CM;
+        for (int ch = 0; ch < nch; ++ch) {
+          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + R0 + ch * CM, sq_row0 + R0, 0, nk);
+          else w2_mma_call(tp, tmem_u, xb, nk);
+        }
+      }
+      // the workers publish the outcome of the factorisation (first failing column or -1) between two CTA-wide barriers
+      asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+      const int fcol = *reinterpret_cast<volatile int*>(c.flag);
+      asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+      if (fcol < 0) break;
+      if (attempt >= p.max_tries || !(p.jitter > 0.f)) break;
+    }
+    if (p.do_inverse) {
+      for (int i = 1; i < nb; ++i) {
+        const int R0 = i * NB;
+        const int nch = (R0 + CM - 1) / CM;
+        for (int ch = 0; ch < nch; ++ch) {
+          const int m_base = ch * CM, nk = (R0 - m_base) / 16;
+          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + m_base, sq_row0 + R0, m_base, nk);
+          else w2_mma_call(tp, tmem_u, xb, nk);
+        }
+      }
+    }
+  }
+}
+
+template <bool TRI, bool HOSTIN = false, int TMA = 0>
+__global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
+    mll_batched_tc_kernel(MllParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+  static_assert(!(TRI && TMA), "the TMA instances are two-CTA instances");
+  static_assert(!(HOSTIN && TMA), "the host-buffer entry uses the register-staged instances");
+  constexpr bool PARK = TRI || TMA != 0;   // chunk-0 panel rows wait in the accumulator columns during the diagonal factorisation
   constexpr uint32_t LOFF = TMA ? W_L_OFF : (TRI ? Y_L_OFF : L_OFF), CTOFF = TMA ? W_CT_OFF : (TRI ? Y_CT_OFF : CT_OFF);
   constexpr uint32_t VECOFF = TMA ? W_VEC_OFF : (TRI ? Y_VEC_OFF : VEC_OFF);
   constexpr uint32_t XTMP = TRI ? Y_TMP : X_TMP, TCOLS = TRI ? T3_COLS : TM_COLS;
@@ -116,6 +158,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   TmaPipe tp;
   tp.full = reinterpret_cast<uint64_t*>(c.red + 44);
   tp.done = tp.full + W_RING;
+  tp.ready = tp.done + W_RING;
   tp.g = 0;
 #ifdef VOLT_PROFILE
   for (int i = 0; i < 8; ++i) tp.prof[i] = 0;
@@ -123,17 +166,26 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   if (tid == 0) {
     mbar_init(c.bar, 1);
     mbar_init(c.bar + 1, 1);
-    if constexpr (TMA) {
-      for (int i = 0; i < W_RING; ++i) { mbar_init(tp.full + i, 1); mbar_init(tp.done + i, 1); }
+    if constexpr (TMA != 0) {
+      for (int i = 0; i < W_RING; ++i) { mbar_init(tp.full + i, 1); mbar_init(tp.done + i, 1); mbar_init(tp.ready + i, NT / 32); }
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();     // every thread of the CTA, control warps included
   tc_fence_after();
   c.tmem = *s_tmem_p;
+  if constexpr (TMA == 2) {
+    const int wu = uniform_warp_id();
+    if (wu >= NT / 32) {
+      w2_control(p, c, tp, &tmA, &tmB, wu);
+      tc_fence_before();
+      __syncthreads();   // pairs with the workers' barrier before the TMEM deallocation
+      return;
+    }
+  }
   const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
   const int sq_row0 = (int)blockIdx.x * p.Tp;   // first row of this CTA's scratch square in the tensor maps
 
@@ -169,7 +221,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
       logdet_part = 0.f;
       if (tid == 0) *c.flag = -1;
       for (int i = tid; i < Tp; i += NT) { c.z[i] = 0.f; c.al[i] = 0.f; if (has2) c.z2[i] = 0.f; }
-      __syncthreads();
+      wsync();
       fail = 0;
       // =============================== Phase A
       for (int j = 0; j < nb; ++j) {
@@ -180,7 +232,8 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
           const int gr = r_base + row;
           TICK(0);
           bool have;
-          if constexpr (TMA) have = gemm_tma<false>(c, tp, &tmA, &tmB, sq_row0, r_base, Tp, R0, 0, R0);
+          if constexpr (TMA == 2) have = gemm_w2_worker<false>(c, tp, r_base, Tp, 0, R0);
+          else if constexpr (TMA == 1) have = gemm_tma<false>(c, tp, &tmA, &tmB, sq_row0, r_base, Tp, R0, 0, R0);
           else if constexpr (TRI) have = gemm_tc1<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           else have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           TICK(1);
@@ -219,7 +272,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
 #pragma unroll
               for (int q = 0; q < 8; ++q) stash[q * 128 + slot] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
-            __syncthreads();
+            wsync();
             TICK(3);
             diag64_block_v2<CLD>(c.Ct, LiT, tmpbuf, c.diagl, c.tmp, c.flag, R0);
             TICK(4);
@@ -229,10 +282,10 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
               // TMA instance: the diagonal block of the scratch holds the block of U = (L^-1)^T instead of L_jj (nothing reads
               // L_jj from the scratch again; the launcher keeps callers that want L out of this instance), so that phase B's
               // operand tiles are plain rectangles of the scratch
-              S[(size_t)(R0 + r) * ld + R0 + cc] = TMA ? LiT[r * CLD + cc] : ((cc <= r) ? c.Ct[r * CLD + cc] : 0.f);
+              S[(size_t)(R0 + r) * ld + R0 + cc] = TMA != 0 ? LiT[r * CLD + cc] : ((cc <= r) ? c.Ct[r * CLD + cc] : 0.f);
               dinv[((size_t)j * NB + r) * NB + cc] = LiT[r * CLD + cc];
             }
-            if constexpr (PARK) __syncthreads();   // D aliases the Linv operand: every read of L_jj precedes the staging
+            if constexpr (PARK) wsync();   // D aliases the Linv operand: every read of L_jj precedes the staging
             stage_linv_from_lit(c, LiT);
             if (rb) {
               const int cz = tid >> 2, part = tid & 3;
@@ -255,7 +308,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
                 c.tmp[cz] = ((R0 + cz < T) ? rb[R0 + cz] : 0.f) - a1;
                 c.tmp[NB + cz] = ((rb2 && R0 + cz < T) ? rb2[R0 + cz] : 0.f) - a2;
               }
-              __syncthreads();
+              wsync();
               if (tid < (has2 ? 2 : 1) * NB) {
                 const int cc = tid & 63, which = tid >> 6;
                 float zz = 0.f;
@@ -277,7 +330,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
 #pragma unroll
               for (int q = 0; q < 32; ++q) s[q] = 0.f;
             }
-            __syncthreads();  // LiT / tmp / stash (aliasing X) are dead from here on; Linv operand staged
+            wsync();  // LiT / tmp / stash (aliasing X) are dead from here on; Linv operand staged
           }
           TICK(5);
           float o[32];
@@ -292,11 +345,15 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
               else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
             }
           }
-          __syncthreads();
+          wsync();
         }
       }
       const int fcol = *c.flag;
-      __syncthreads();
+      if constexpr (TMA == 2) {   // the control warps read the outcome between these two barriers (w2_control)
+        asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+      }
+      wsync();
       if (fcol < 0) break;
       fail = fcol + 1;
       if (attempt >= p.max_tries || !(p.jitter > 0.f)) break;
@@ -315,7 +372,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
           const int r = idx >> 4, c4 = (idx & 15) * 4;
           *reinterpret_cast<float4*>(LiT + r * CLD + c4) = *reinterpret_cast<const float4*>(Di + r * NB + c4);
         }
-        __syncthreads();
+        wsync();
         stage_linv_from_lit(c, LiT);
         for (int idx = tid; idx < NB * NB; idx += NT) {
           const int m = idx >> 6, cc = idx & 63;
@@ -329,13 +386,14 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
           for (int cc = tid; cc < NB; ++cc) a = fmaf(LiT[tid * CLD + cc], c.z[R0 + cc], a);
           c.al[R0 + tid] += a;
         }
-        __syncthreads();
+        wsync();
         const int nch = (R0 + CM - 1) / CM;
         for (int ch = 0; ch < nch; ++ch) {
           const int m_base = ch * CM;
           const int m = m_base + row;
           TICK(7);
-          if constexpr (TMA) gemm_tma<true>(c, tp, &tmA, &tmB, sq_row0, m_base, R0, R0, m_base, R0);
+          if constexpr (TMA == 2) gemm_w2_worker<true>(c, tp, m_base, R0, m_base, R0);
+          else if constexpr (TMA == 1) gemm_tma<true>(c, tp, &tmA, &tmB, sq_row0, m_base, R0, R0, m_base, R0);
           else if constexpr (TRI) gemm_tc1<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
           else gemm_tc<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
           TICK(8);
@@ -365,9 +423,9 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
             if (half_id) c.tmp[row] = dot;   // the two column halves of a row are combined in a fixed order
             else hdot = dot;
           }
-          __syncthreads();
+          wsync();
           if (m < R0 && half_id == 0) c.al[m] += hdot + c.tmp[row];
-          __syncthreads();
+          wsync();
         }
       }
     }
@@ -385,13 +443,13 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
       if (rb) ar = fmaf(ai, rb[i], ar);
       if (p.alpha && p.do_inverse) p.alpha[(size_t)b * T + i] = ai;
     }
-    const float inv_quad = block_sum(zz, c.red);
-    const float logdet = 2.f * block_sum(logdet_part, c.red);
-    const float tr_inv = block_sum(tr_part, c.red);
-    const float alal = block_sum(aa, c.red);
-    const float alr = block_sum(ar, c.red);
-    const float sz22 = block_sum(z22, c.red);
-    const float sz12 = block_sum(z12, c.red);
+    const float inv_quad = block_sum_w(zz, c.red);
+    const float logdet = 2.f * block_sum_w(logdet_part, c.red);
+    const float tr_inv = block_sum_w(tr_part, c.red);
+    const float alal = block_sum_w(aa, c.red);
+    const float alr = block_sum_w(ar, c.red);
+    const float sz22 = block_sum_w(z22, c.red);
+    const float sz12 = block_sum_w(z12, c.red);
     if (tid == 0) {
       if (p.scalars) {
         float* o = p.scalars + (size_t)b * NSCALARS;
@@ -425,7 +483,7 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
         Lo[(size_t)r * p.ldl + cc] = (cc <= r) ? S[(size_t)r * ld + cc] : 0.f;
       }
     }
-    __syncthreads();
+    wsync();
   }
 
   if (p.loss_out) {
@@ -433,17 +491,17 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
     // values in a fixed order (thread t takes b = t, t + 256, ...; then the block reduction), so the result does not
     // depend on which CTA happens to be last.
     __threadfence();
-    __syncthreads();
+    wsync();
     if (tid == 0) {
       const unsigned int ticket = atomicAdd(p.done_counter, 1u);
       *c.flag = (ticket == gridDim.x - 1) ? 1 : 0;
     }
-    __syncthreads();
+    wsync();
     if (*c.flag) {
       __threadfence();
       float acc = 0.f;
       for (int b = tid; b < p.B; b += NT) acc += __ldcg(p.scalars + (size_t)b * NSCALARS);
-      const float tot = block_sum(acc, c.red);
+      const float tot = block_sum_w(acc, c.red);
       if (tid == 0) {
         p.loss_out[0] = -tot;
         *p.done_counter = 0u;   // ready for the next launch on this stream
@@ -455,11 +513,11 @@ __global__ void __launch_bounds__(NT, TRI ? 3 : 2) mll_batched_tc_kernel(MllPara
   if (tid == 0 && blockIdx.x == 0 && p.z_out == nullptr && p.alpha) {
     for (int i = 0; i < 12; ++i) p.alpha[i] = (float)seg[i];
     for (int i = 0; i < 8; ++i) { p.alpha[12 + i] = (float)g_diag_prof[i]; g_diag_prof[i] = 0; }
-    if constexpr (TMA) for (int i = 0; i < 8; ++i) p.alpha[20 + i] = (float)tp.prof[i];
+    if constexpr (TMA != 0) for (int i = 0; i < 8; ++i) p.alpha[20 + i] = (float)tp.prof[i];
   }
 #endif
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();     // every thread of the CTA (the control warps of the TMA = 2 instance wait here too)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(TCOLS) : "memory");
 }
 
@@ -495,7 +553,7 @@ static int encode_scratch_map(CUtensorMap* map, float* base, int Tp, long long r
   return VOLT_OK;
 }
 
-template <bool TRI, bool HOSTIN, bool TMA = false>
+template <bool TRI, bool HOSTIN, int TMA = 0>
 static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   static size_t attr_smem_dev[16] = {};   // function attributes are per device
   size_t& attr_smem = attr_smem_dev[device_slot()];
@@ -523,14 +581,14 @@ static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
     s = encode_scratch_map(&tmB, p.scratch, p.Tp, (long long)grid * p.Tp, 64);
     if (s) return s;
   }
-  tc::mll_batched_tc_kernel<TRI, HOSTIN, TMA><<<grid, NT, smem, st>>>(p, tmA, tmB);
+  tc::mll_batched_tc_kernel<TRI, HOSTIN, TMA><<<grid, TMA == 2 ? tc::W2_THREADS : NT, smem, st>>>(p, tmA, tmB);
   return check_cuda(cudaGetLastError(), "mll_batched_tc_kernel");
 }
 
 // resident CTAs (= series in flight) of the batched kernel for series of length T: the first wave of a batch
 int mll_tc_resident_ctas(int T, int two_rhs) {
   const int Tp = (T + NB - 1) / NB * NB;
-  const size_t vec = sizeof(float) * (size_t)((two_rhs ? 4 : 3) * Tp + NB + 2 * NB + 32 + 12 + 20);
+  const size_t vec = sizeof(float) * (size_t)((two_rhs ? 4 : 3) * Tp + NB + 2 * NB + 32 + 12 + 32);
   const size_t smem3 = tc::Y_VEC_OFF + vec;
   if (3 * (smem3 + 1024) <= 233472) return 3 * sm_count();
   const size_t smem = tc::VEC_OFF + vec;
@@ -539,8 +597,8 @@ int mll_tc_resident_ctas(int T, int two_rhs) {
 }
 
 // Default choice between the register-staged instances and the TMA-fed one, from measurements on the B200.
-// B200, one launch (ms): 256 x T=1024: 2.41 TMA vs 2.87 register-staged; 296 x 512: 0.538 vs 0.551; 148 x 512: 0.430 both;
-// 444 x 512: 0.906 vs 0.776 and 1024 x 512: 1.86 vs 1.82 for the three-CTA register-staged instance, which keeps those.
+// B200, one launch (ms), control-warp TMA instance vs register-staged: 256 x T=1024: 2.34 vs 2.87; 296 x 512: 0.536 vs 0.551;
+// 148 x 512: 0.424 vs 0.430; 1024 x 512: 1.83 vs 1.82 for the three-CTA register-staged instance, which keeps the full waves.
 static bool use_tma_default(int B, int T, int sms) {
   const int Tp = (T + NB - 1) / NB * NB;
   if (Tp > 832) return true;                        // no three-CTA instance at this length
@@ -550,7 +608,7 @@ static bool use_tma_default(int B, int T, int sms) {
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.Tp = (p.T + NB - 1) / NB * NB;
   p.nb = p.Tp / NB;
-  const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12 + 20);
+  const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12 + 32);
   const size_t smem_total = 233472, smem_cta_reserved = 1024;   // sm_100: 228 KB per SM, 1 KB reserved per resident CTA
   // three resident CTAs per SM when the small shared-memory map fits three times (T <= 832); VOLT_TC_CTAS=2 / 3 forces the
   // double-buffered two-CTA / the three-CTA kernel (A/B timing)
@@ -567,7 +625,9 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
     static const int tma_first = [] { const char* e = getenv("VOLT_TC_TMA"); return e ? atoi(e) : -1; }();
     const size_t smem_w0 = tc::W_VEC_OFF + vec;
     if (tma_first == 2 && !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total)
-      return launch_tc<false, false, true>(p, st, smem_w0, 2);   // VOLT_TC_TMA=2: force the TMA instance (A/B timing)
+      return launch_tc<false, false, 2>(p, st, smem_w0, 2);      // VOLT_TC_TMA=2: force the control-warp TMA instance (A/B timing)
+    if (tma_first == 3 && !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total)
+      return launch_tc<false, false, 1>(p, st, smem_w0, 2);      // VOLT_TC_TMA=3: the in-line TMA instance
   }
   const bool prefer2 = forced != 3 && ((p.B <= 2 * sms) || (p.B > 3 * sms && p.B <= 4 * sms));
   if (!force2 && !prefer2 && 3 * (smem3 + smem_cta_reserved) <= smem_total)
@@ -578,7 +638,7 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   const size_t smem_w = tc::W_VEC_OFF + vec;
   const bool tma_ok = !hostin && !p.L_out && 2 * (smem_w + smem_cta_reserved) <= smem_total;
   const bool want_tma = tma_env == 2 || (tma_env != 0 && use_tma_default(p.B, p.T, sms));
-  if (tma_ok && want_tma && (forced != 2 || tma_env == 2)) return launch_tc<false, false, true>(p, st, smem_w, 2);
+  if (tma_ok && want_tma && (forced != 2 || tma_env == 2)) return launch_tc<false, false, 2>(p, st, smem_w, 2);
   const size_t smem = tc::VEC_OFF + vec;
   if (smem > 227 * 1024) {
     set_error("mll_batched_tc: T=%d needs %zu bytes of shared memory (max 227 KB)", p.T, smem);

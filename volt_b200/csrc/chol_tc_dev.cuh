@@ -212,7 +212,7 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
       st_split(BH, BL, idx >> 3, idx & 7, rb[i]);
     }
     if (kt + 1 < nk) gload(k_lo + (kt + 1) * 32);
-    __syncthreads();
+    wsync();
     {
       uint32_t hi[16], lo[16];
 #pragma unroll
@@ -232,7 +232,7 @@ __device__ bool gemm_tc(Ctx& c, const float* S, int ld, int a_row0, int a_row_en
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    wsync();
     if (wu == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -275,7 +275,7 @@ static __device__ void trsm_tc(Ctx& c, const float (&s)[32], float (&o)[32], int
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  wsync();
   if (uniform_warp_id() == 0) {
     tc_fence_after();
     const uint32_t tmem_u = make_uniform(c.tmem);
@@ -363,7 +363,7 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
       gload_b(k_lo + (kt + 1) * 32);
       gload_a(k_lo + (kt + 1) * 32);
     }
-    __syncthreads();
+    wsync();
     {
       uint32_t hi[16], lo[16];
 #pragma unroll
@@ -383,7 +383,7 @@ __device__ bool gemm_tc1(Ctx& c, const float* S, int ld, int a_row0, int a_row_e
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    wsync();
     if (wu == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -428,7 +428,7 @@ static __device__ void trsm_tc1(Ctx& c, const float (&s)[32], float (&o)[32], in
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    wsync();
     if (wu == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -510,14 +510,15 @@ constexpr int W_RING = 4;
 constexpr uint32_t HA_TILE = 128u * 64u, HB_TILE = 64u * 64u;      // bytes: 128 x 16 floats, 64 x 16 floats
 constexpr uint32_t W_SLOT = HA_TILE + HB_TILE;                     // 12 KB
 constexpr uint32_t W_BL = W_RING * W_SLOT;                         // two B lo tiles after the ring
-constexpr int W_BLN = 3;                                           // B lo tiles / TMEM A stages cycle with period 3 (see gemm_tma)
-constexpr uint32_t W_BYTES = W_BL + W_BLN * HB_TILE;               // 60 KB; aliased by LiT | diag scratch and the store tiles
+constexpr int W_BLN = 4;                                           // B lo tiles / TMEM A stages: one per ring slot
+constexpr uint32_t W_BYTES = W_BL + W_BLN * HB_TILE;               // 64 KB; aliased by LiT | diag scratch and the store tiles
 constexpr uint32_t W_L_OFF = W_BYTES, W_CT_OFF = W_L_OFF, W_VEC_OFF = W_L_OFF + L_BYTES;   // D aliases the Linv operand
 static_assert(X_TMP + DIAG2_SCRATCH_FLOATS * 4 <= W_BYTES && 8 * 1152 * 4 <= W_BYTES, "diag scratch / store tiles must fit the ring region");
 
 struct TmaPipe {
   uint64_t* full;    // [W_RING] TMA landed
   uint64_t* done;    // [W_RING] MMAs of the tile that used the slot have completed
+  uint64_t* ready;   // [W_RING] (control-warp instance) the workers have split the tile: one arrival per worker warp
   uint32_t g;        // running k-tile counter of this CTA (slot = g % W_RING, use = g / W_RING)
 #ifdef VOLT_PROFILE
   long long prof[8];
@@ -576,7 +577,7 @@ __device__ bool gemm_tma(Ctx& c, TmaPipe& tp, const void* tmA, const void* tmB, 
   long long wlast = clock64();
 #endif
   fence_proxy_async_all();
-  __syncthreads();
+  wsync();
   WTICK(0);
   const uint32_t g0 = tp.g;
   // Two elected lanes in different warps share the asynchronous work of a k-tile: one lane of warp 0 issues the MMAs, one
@@ -638,7 +639,7 @@ __device__ bool gemm_tma(Ctx& c, TmaPipe& tp, const void* tmA, const void* tmB, 
     WTICK(4);
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    wsync();
     WTICK(5);
     if (wu == 0) {
       tc_fence_after();
@@ -675,6 +676,121 @@ __device__ bool gemm_tma(Ctx& c, TmaPipe& tp, const void* tmA, const void* tmB, 
   WTICK(6);
   tc_fence_after();
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Control-warp form of the TMA-fed loop (the "W2" instance: 256 worker threads + warp 8 = MMA issuer + warp 9 = TMA producer).
+// In gemm_tma the warp that issues the MMAs also has its share of the split work, so every k-tile pays for its issue
+// section (~350 cycles: the UTCHMMAs queue behind the tensor pipe) on the critical path, and for a CTA barrier.  Here the
+// three roles only meet on mbarriers:
+//     TMA producer:  [t >= RING: wait done(t - RING)]  ->  cp.async.bulk.tensor of k-tile t into slot t % RING  -> full(t)
+//     workers:       wait full(t) -> split (A: smem -> TMEM hi / lo, B: lo tile) -> one arrival per warp on ready(t)
+//     MMA issuer:    wait ready(t) -> 6 x tcgen05.mma -> tcgen05.commit -> done(t)
+// full(t) implies that the MMAs of tile t - RING have completed (the producer waited for them), which is what makes slot,
+// TMEM stage and B lo tile t % RING free to be overwritten: the workers need no other wait inside the loop, and no barrier.
+// The control warps follow the same deterministic schedule of GEMM calls as the workers (chol_tc.cu: w2_control).
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_workers_tma() { asm volatile("bar.sync 3, 288;" ::: "memory"); }   // 256 workers + the TMA warp
+
+template <bool PHASE_B>
+__device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, int k_lo, int k_hi) {
+  const int nk = (k_hi - k_lo) / 16;
+  if (nk <= 0) return false;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int row = 32 * (w & 3) + lane, half_id = w >> 2;
+  const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  // earlier global writes (panel stores, diagonal blocks) -> visible to the async proxy; the ring region may have been the
+  // epilogue's scratch.  The producer starts this call's loads after the barrier.
+  fence_proxy_async_all();
+  bar_workers_tma();
+  const uint32_t g0 = tp.g;
+  const bool row_ok = (a_row0 + row) < a_row_end;
+  const int mb = (a_row0 + row) >> 6;
+  for (int kt = 0; kt < nk; ++kt) {
+    const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
+    const uint8_t* RAW = c.X + s * W_SLOT;
+    const uint8_t* BH = RAW + HA_TILE;
+    uint8_t* BL = c.X + W_BL + s * HB_TILE;
+    mbar_wait(tp.full + s, (g / W_RING) & 1u);
+    uint32_t hi[8], lo[8];
+    const bool live = row_ok && !(PHASE_B && ((k_lo + 16 * kt) >> 6) < mb);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(RAW + swz64(row, 2 * half_id + q));
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t u = live ? __float_as_uint(e[j]) : 0u;
+        hi[4 * q + j] = u;
+        lo[4 * q + j] = __float_as_uint(__uint_as_float(u) - __uint_as_float(u & 0xffffe000u));
+      }
+    }
+    tmem_st8(c.tmem + lane_base + TM_PHI + (uint32_t)(16 * s + 8 * half_id), hi);
+    tmem_st8(c.tmem + lane_base + TM_PLO + (uint32_t)(16 * s + 8 * half_id), lo);
+    const uint32_t off = swz64(tid >> 2, tid & 3);
+    const float4 b = *reinterpret_cast<const float4*>(BH + off);
+    float4 l;
+    l.x = b.x - __uint_as_float(__float_as_uint(b.x) & 0xffffe000u);
+    l.y = b.y - __uint_as_float(__float_as_uint(b.y) & 0xffffe000u);
+    l.z = b.z - __uint_as_float(__float_as_uint(b.z) & 0xffffe000u);
+    l.w = b.w - __uint_as_float(__float_as_uint(b.w) & 0xffffe000u);
+    *reinterpret_cast<float4*>(BL + off) = l;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tp.ready + s);
+  }
+  tp.g = g0 + (uint32_t)nk;
+  {
+    const uint32_t gl = g0 + (uint32_t)nk - 1u;     // the last commit covers every MMA issued before it
+    mbar_wait(tp.done + (gl % W_RING), (gl / W_RING) & 1u);
+  }
+  tc_fence_after();
+  return true;
+}
+
+// TMA producer warp: every lane takes the call-start barrier, one elected lane issues the loads
+__device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const void* tmB, uint32_t xb, int row_a, int row_b, int k_lo, int nk) {
+  bar_workers_tma();
+  const uint32_t g0 = tp.g;
+  if (elect_one()) {
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
+      if (kt >= W_RING) mbar_wait(tp.done + s, ((g - W_RING) / W_RING) & 1u);    // MMAs of the slot's previous tile (this call)
+      mbar_expect_tx(tp.full + s, W_SLOT);
+      tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, k_lo + 16 * kt, row_a);
+      tma_load_2d(tmB, xb + s * W_SLOT + HA_TILE, tp.full + s, k_lo + 16 * kt, row_b);
+    }
+  }
+  __syncwarp();
+  tp.g = g0 + (uint32_t)nk;
+}
+
+// MMA issuer warp
+__device__ __forceinline__ void w2_mma_call(TmaPipe& tp, uint32_t tmem_u, uint32_t xb, int nk) {
+  const uint32_t g0 = tp.g;
+  if (elect_one()) {
+    for (int kt = 0; kt < nk; ++kt) {
+      const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
+      mbar_wait(tp.ready + s, (g / W_RING) & 1u);
+      tc_fence_after();
+      const uint64_t dbh = make_desc64(xb + s * W_SLOT + HA_TILE), dbl = make_desc64(xb + W_BL + s * HB_TILE);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint64_t adv = (uint64_t)(2 * ks);
+        const uint32_t ah = tmem_u + TM_PHI + 16 * s + 8 * ks, al = tmem_u + TM_PLO + 16 * s + 8 * ks;
+        umma_tf32_ts(tmem_u + TM_ACC0, al, dbh + adv, (kt == 0 && ks == 0) ? 0u : 1u);
+        umma_tf32_ts(tmem_u + TM_ACC0, ah, dbl + adv, 1u);
+        umma_tf32_ts(tmem_u + TM_ACC0, ah, dbh + adv, 1u);
+      }
+      umma_commit(tp.done + s);
+    }
+  }
+  __syncwarp();
+  tp.g = g0 + (uint32_t)nk;
 }
 
 // A-generator for one accumulator row: s[q] <- A[gr][gc0 + q] - s[q], q = 0..31.  Fast path (no identity padding, on-the-fly
