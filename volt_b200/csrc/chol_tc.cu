@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
           const int gr = r_base + row;
           TICK(0);
           bool have;
-          if constexpr (TMA == 2) have = gemm_w2_worker<false>(c, tp, r_base, Tp, 0, R0);
+          if constexpr (TMA == 2) have = gemm_w2_worker<false>(c, tp, r_base, Tp, 0, R0, ch == 0);
           else if constexpr (TMA == 1) have = gemm_tma<false>(c, tp, &tmA, &tmB, sq_row0, r_base, Tp, R0, 0, R0);
           else if constexpr (TRI) have = gemm_tc1<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           else have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
           const int m_base = ch * CM;
           const int m = m_base + row;
           TICK(7);
-          if constexpr (TMA == 2) gemm_w2_worker<true>(c, tp, m_base, R0, m_base, R0);
+          if constexpr (TMA == 2) gemm_w2_worker<true>(c, tp, m_base, R0, m_base, R0, ch == 0);
           else if constexpr (TMA == 1) gemm_tma<true>(c, tp, &tmA, &tmB, sq_row0, m_base, R0, R0, m_base, R0);
           else if constexpr (TRI) gemm_tc1<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
           else gemm_tc<true>(c, S, ld, m_base, R0, R0, m_base, R0, dinv);
@@ -597,12 +597,13 @@ int mll_tc_resident_ctas(int T, int two_rhs) {
 }
 
 // Default choice between the register-staged instances and the TMA-fed one, from measurements on the B200.
-// B200, one launch (ms), control-warp TMA instance vs register-staged: 256 x T=1024: 2.34 vs 2.87; 296 x 512: 0.536 vs 0.551;
-// 148 x 512: 0.424 vs 0.430; 1024 x 512: 1.83 vs 1.82 for the three-CTA register-staged instance, which keeps the full waves.
+// B200, one launch (ms), control-warp TMA instance vs the register-staged instances (two / three CTAs per SM):
+// 1024 x 512: 1.75 vs 1.81; 256 x 1024: 2.27 vs 2.84; 296 x 512: 0.514 vs 0.565; 148 x 512: 0.397 vs 0.431.
+// Short series are dominated by the diagonal blocks, where a third resident CTA per SM helps more than a faster GEMM loop:
+// 2048 x 256: 0.97 vs 0.89; 4096 x 128: 0.76 vs 0.64 -- those stay on the three-CTA register-staged instance.
 static bool use_tma_default(int B, int T, int sms) {
-  const int Tp = (T + NB - 1) / NB * NB;
-  if (Tp > 832) return true;                        // no three-CTA instance at this length
-  return B > sms && B <= 2 * sms;                   // two series per SM: the two-CTA instances, TMA-fed
+  (void)B; (void)sms;
+  return (T + NB - 1) / NB * NB >= 448;
 }
 
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
@@ -624,8 +625,9 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   {
     static const int tma_first = [] { const char* e = getenv("VOLT_TC_TMA"); return e ? atoi(e) : -1; }();
     const size_t smem_w0 = tc::W_VEC_OFF + vec;
-    if (tma_first == 2 && !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total)
-      return launch_tc<false, false, 2>(p, st, smem_w0, 2);      // VOLT_TC_TMA=2: force the control-warp TMA instance (A/B timing)
+    const bool eligible = !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total;
+    if (eligible && forced == 0 && (tma_first == 2 || (tma_first < 0 && use_tma_default(p.B, p.T, sms))))
+      return launch_tc<false, false, 2>(p, st, smem_w0, 2);      // the control-warp TMA instance (VOLT_TC_TMA=0 / VOLT_TC_CTAS: A/B timing)
     if (tma_first == 3 && !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total)
       return launch_tc<false, false, 1>(p, st, smem_w0, 2);      // VOLT_TC_TMA=3: the in-line TMA instance
   }

@@ -61,15 +61,22 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or a time limit expires; with the default (short)
+// limit a waiting warp re-issues the instruction continuously -- 13 % (register-staged instances) to 26 % (control-warp
+// instance) of all executed instructions were these retries, taken from the issue slots of the warps that had work.  The
+// explicit limit (suspendTimeHint, ns) keeps a waiter asleep until the mbarrier wakes it.
+#ifndef VOLT_MBAR_HINT_NS
+#define VOLT_MBAR_HINT_NS 200000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra D_%=;\n\t"
       "bra W_%=;\n\t"
       "D_%=:\n\t}" ::"r"(s_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"((uint32_t)VOLT_MBAR_HINT_NS)
       : "memory");
 }
 // 32 consecutive accumulator columns of this thread's TMEM lane (warp w reads lanes 32 (w%4) .. +31)
@@ -545,7 +552,9 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t dst, uint
       "l"(tmap), "r"(s_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes -> async proxy (TMA): global (panel stores that a later tensor-map load reads) and this CTA's shared
+// memory (ring slots that served as scratch)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
@@ -576,7 +585,8 @@ __device__ bool gemm_tma(Ctx& c, TmaPipe& tp, const void* tmA, const void* tmB, 
 #ifdef VOLT_PROFILE
   long long wlast = clock64();
 #endif
-  fence_proxy_async_all();
+  fence_proxy_async_global();
+  fence_async_smem();
   wsync();
   WTICK(0);
   const uint32_t g0 = tp.g;
@@ -694,8 +704,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void bar_workers_tma() { asm volatile("bar.sync 3, 288;" ::: "memory"); }   // 256 workers + the TMA warp
 
+// dep: the call reads global data written since the previous call with dep = true (first chunk of a block step: the
+// panel / inverse block column of the step before); the other chunks of a step only read older columns.
 template <bool PHASE_B>
-__device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, int k_lo, int k_hi) {
+__device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, int k_lo, int k_hi, bool dep) {
   const int nk = (k_hi - k_lo) / 16;
   if (nk <= 0) return false;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -703,7 +715,8 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
   const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
   // earlier global writes (panel stores, diagonal blocks) -> visible to the async proxy; the ring region may have been the
   // epilogue's scratch.  The producer starts this call's loads after the barrier.
-  fence_proxy_async_all();
+  if (dep) fence_proxy_async_global();
+  fence_async_smem();
   bar_workers_tma();
   const uint32_t g0 = tp.g;
   const bool row_ok = (a_row0 + row) < a_row_end;
@@ -713,7 +726,7 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
     const uint8_t* RAW = c.X + s * W_SLOT;
     const uint8_t* BH = RAW + HA_TILE;
     uint8_t* BL = c.X + W_BL + s * HB_TILE;
-    mbar_wait(tp.full + s, (g / W_RING) & 1u);
+    mbar_wait(tp.full + s, (g / W_RING) & 1u);   // (probing the next tile's barrier early with test_wait was measured: +2 %)
     uint32_t hi[8], lo[8];
     const bool live = row_ok && !(PHASE_B && ((k_lo + 16 * kt) >> 6) < mb);
 #pragma unroll
