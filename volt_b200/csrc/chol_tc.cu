@@ -76,12 +76,19 @@ constexpr int W2_THREADS = NT + 64;
 
 // Control warps of the TMA = 2 instance: they walk the same deterministic schedule of GEMM calls as the workers (series loop,
 // psd_safe_cholesky attempts, phase A block steps x row chunks, phase B) and feed / issue every k-tile of every call.
+template <bool HOSTIN>
 __device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtensorMap* tmA, const CUtensorMap* tmB, int wu) {
   const int Tp = p.Tp, nb = p.nb;
   const uint32_t xb = s_u32(c.X), tmem_u = make_uniform(c.tmem);
   const int sq_row0 = (int)blockIdx.x * Tp;
   const bool is_tma = (wu == 9);
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    if (HOSTIN) {   // host-buffer entry: the workers report whether this series' inputs arrived (they stop if not)
+      asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+      const int arrived = *reinterpret_cast<volatile int*>(c.flag + 1);
+      asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+      if (!arrived) break;
+    }
     for (int attempt = 0;; ++attempt) {
       for (int j = 1; j < nb; ++j) {                       // block step 0 has no earlier columns: no GEMM call
         const int R0 = j * NB, nk = R0 / 16;
@@ -116,7 +123,7 @@ template <bool TRI, bool HOSTIN = false, int TMA = 0>
 __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
     mll_batched_tc_kernel(MllParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   static_assert(!(TRI && TMA), "the TMA instances are two-CTA instances");
-  static_assert(!(HOSTIN && TMA), "the host-buffer entry uses the register-staged instances");
+  static_assert(!(HOSTIN && TMA == 1), "the host-buffer entry uses the register-staged or the control-warp instance");
   constexpr bool PARK = TRI || TMA != 0;   // chunk-0 panel rows wait in the accumulator columns during the diagonal factorisation
   constexpr uint32_t LOFF = TMA ? W_L_OFF : (TRI ? Y_L_OFF : L_OFF), CTOFF = TMA ? W_CT_OFF : (TRI ? Y_CT_OFF : CT_OFF);
   constexpr uint32_t VECOFF = TMA ? W_VEC_OFF : (TRI ? Y_VEC_OFF : VEC_OFF);
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
   if constexpr (TMA == 2) {
     const int wu = uniform_warp_id();
     if (wu >= NT / 32) {
-      w2_control(p, c, tp, &tmA, &tmB, wu);
+      w2_control<HOSTIN>(p, c, tp, &tmA, &tmB, wu);
       tc_fence_before();
       __syncthreads();   // pairs with the workers' barrier before the TMEM deallocation
       return;
@@ -195,9 +202,15 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
 #endif
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (HOSTIN) {
-      if (!hostin_prologue((p.ready && b >= p.ready_from) ? p.ready : nullptr, p.ready_timeout, p.ready_spins,
-                           p.x_in + (p.x_batched ? (size_t)b * T : 0), p.vol_in + (size_t)b * T, T, Tp, p.vol_mode, c.Vs, c.flag))
-        break;
+      const bool arrived = hostin_prologue((p.ready && b >= p.ready_from) ? p.ready : nullptr, p.ready_timeout, p.ready_spins,
+                                           p.x_in + (p.x_batched ? (size_t)b * T : 0), p.vol_in + (size_t)b * T, T, Tp, p.vol_mode, c.Vs,
+                                           c.flag);
+      if constexpr (TMA == 2) {   // tell the control warps (w2_control)
+        if (tid == 0) c.flag[1] = arrived ? 1 : 0;
+        asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
+      }
+      if (!arrived) break;
     } else {
       for (int i = tid; i < Tp; i += NT) {
         float v = 0.f;
@@ -625,9 +638,9 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   {
     static const int tma_first = [] { const char* e = getenv("VOLT_TC_TMA"); return e ? atoi(e) : -1; }();
     const size_t smem_w0 = tc::W_VEC_OFF + vec;
-    const bool eligible = !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total;
-    if (eligible && forced == 0 && (tma_first == 2 || (tma_first < 0 && use_tma_default(p.B, p.T, sms))))
-      return launch_tc<false, false, 2>(p, st, smem_w0, 2);      // the control-warp TMA instance (VOLT_TC_TMA=0 / VOLT_TC_CTAS: A/B timing)
+    const bool eligible = !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total;
+    if (eligible && forced == 0 && (tma_first == 2 || (tma_first < 0 && use_tma_default(p.B, p.T, sms))))   // VOLT_TC_TMA=0 / VOLT_TC_CTAS: A/B timing
+      return hostin ? launch_tc<false, true, 2>(p, st, smem_w0, 2) : launch_tc<false, false, 2>(p, st, smem_w0, 2);
     if (tma_first == 3 && !hostin && !p.L_out && 2 * (smem_w0 + smem_cta_reserved) <= smem_total)
       return launch_tc<false, false, 1>(p, st, smem_w0, 2);      // VOLT_TC_TMA=3: the in-line TMA instance
   }
