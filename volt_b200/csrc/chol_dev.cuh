@@ -244,6 +244,10 @@ __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, 
   }
 }
 
+// (A second version of this routine -- columns split between the two half-warps, column broadcast through a shared-memory
+// line with broadcast LDS.128 instead of ten shuffles per step, MUFU.RCP on the chain and rsqrt + Newton off it -- was
+// measured in round 2: correct, but 6.7 k instead of 3.4 k cycles per block: with in-order issue the STS -> __syncwarp ->
+// LDS round trip of every step costs more than the shuffles it replaces.)
 __device__ __forceinline__ float dotn(const float* a, const float* b, int n) {  // n multiple of 4, 16-byte aligned
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (int t = 0; t < n; t += 4) {
