@@ -645,10 +645,32 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
   p.V = Vt;
   p.resid2 = Vt;
   p.do_inverse = 0;
+  if (g_mll_impl < 0) {
+    const char* e = getenv("VOLT_MLL_IMPL");
+    g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
+  }
+  // Tensor-core batched kernel: it writes the rollout kernel's per-series inputs itself and raises a flag per series; the
+  // rollout kernel is launched as a programmatic dependent and starts on the finished series while the prep kernel's last
+  // wave is still running.  (Other kernels: pack kernel + plain stream order.)
+  static const int overlap_env = [] { const char* e = getenv("VOLT_ROLLOUT_OVERLAP"); return e ? atoi(e) : 1; }();
+  const bool overlap = overlap_env && g_mll_impl && !(n >= 1536 && B <= 16);
+  int* flags = nullptr;
+  if (overlap) {
+    void* fl_ws = nullptr;
+    s = get_workspace((size_t)B * sizeof(int), &fl_ws, 14, st);
+    if (s) return s;
+    flags = (int*)fl_ws;
+    VOLT_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int), st));
+    p.pack_out = series;
+    p.pack_x = x;
+    p.series_flag = flags;
+  }
   s = launch_mll_batched(p, st);
   if (s) return s;
-  s = launch_rollout_pack(scal, Vt, x, B, n, series, st);
-  if (s) return s;
+  if (!overlap) {
+    s = launch_rollout_pack(scal, Vt, x, B, n, series, st);
+    if (s) return s;
+  }
   RolloutParams q;
   memset(&q, 0, sizeof(q));
   q.B = B; q.n = n; q.S = S; q.H = H; q.k = ma ? k : 0; q.mean_kind = mean_kind; q.joint = joint;
@@ -670,6 +692,7 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
   q.seed = seed;
   q.samples = samples;
   q.info = draw_info;
+  q.series_flag = flags;
   return launch_rollout(q, st);
 }
 

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(s_tmem_p)), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.series_flag) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the rollout kernel may be scheduled behind us
   TmaPipe tp;
   tp.full = reinterpret_cast<uint64_t*>(c.red + 44);
   tp.done = tp.full + W_RING;
@@ -476,6 +477,15 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
         for (int q = 12; q < NSCALARS; ++q) o[q] = 0.f;
       }
       if (p.info) p.info[b] = fail;
+      if (p.pack_out) {   // what the rollout kernel needs of this series (rollout.cu); V[n-1] is still in shared memory
+        float* o = p.pack_out + (size_t)b * NSERIES;
+        o[0] = sz22; o[1] = sz12; o[2] = c.Vs[T - 1]; o[3] = p.pack_x[1] - p.pack_x[0]; o[4] = jit_used;
+        o[5] = o[6] = o[7] = 0.f;
+      }
+      if (p.series_flag) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.series_flag + b), "r"(1) : "memory");
+      }
     }
     if (p.U_out && p.do_inverse) {
       // (L^-1)^T: strictly-upper 64-blocks live in the scratch, the diagonal blocks in dinv (dinv[j][r][c] = Linv_jj[c][r])

@@ -38,6 +38,10 @@ struct MllParams {
   // and the last CTA to finish writes loss_out[0] = -sum_b MLL_b, summed in a fixed order (bitwise reproducible).
   const float* raw_noise; int raw_stride;
   float* loss_out; unsigned int* done_counter;
+  // rollout prep (tensor-core batched kernel): per-series hand-over to the rollout kernel, which is launched as a programmatic
+  // dependent and starts on a series as soon as its flag is raised -- pack_out (B, NSERIES): u.u, u.z1, V[n-1], dx, jitter;
+  // series_flag[b] = 1 (release) once pack_out / info of series b are written
+  float* pack_out; const float* pack_x; int* series_flag;
 };
 
 // [GPyTorch] GaussianLikelihood / GreaterThan(1e-4): noise = softplus(raw_noise) + 1e-4 (torch's softplus: beta 1, threshold 20)
@@ -101,6 +105,7 @@ struct RolloutParams {
   float* samples;          // (B,S,H)
   int* info;               // (B,S) bit0: per-draw pivot failure, bit1: pred_cov needed jitter, bit2: not PSD after jitter
   int Hp;                  // padded tile row length (odd)
+  const int* series_flag;  // (B) or null: wait until series_flag[b] != 0 before reading series / series_info (prep still running)
   int b_offset;            // global index of series 0 of this launch (batches > 65535 series are launched in chunks)
 };
 

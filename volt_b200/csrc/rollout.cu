@@ -159,6 +159,19 @@ __global__ void __launch_bounds__(128) rollout_kernel(RolloutParams p) {
   const int b = blockIdx.y;
   const int s0 = blockIdx.x * TS;
   const int tid = threadIdx.x;
+  if (p.series_flag) {
+    // launched as a programmatic dependent of the prep kernel: wait for THIS series' shared factor only (the prep kernel's
+    // CTAs are all resident before any CTA of this grid can be, so the wait cannot starve them)
+    if (tid == 0) {
+      int f = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.series_flag + b) : "memory");
+        if (f != 0) break;
+        __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
 
   for (int t = tid; t < k; t += TS) sw[t] = p.w ? p.w[t] : 0.f;
   const float* yb = p.ytrain + (size_t)b * n;
@@ -423,8 +436,20 @@ int launch_rollout(RolloutParams p, cudaStream_t st) {
     if (p.mr_latent) q.mr_latent = p.mr_latent + b0;
     q.samples = p.samples + (size_t)b0 * p.S * p.H;
     if (p.info) q.info = p.info + (size_t)b0 * p.S;
+    if (p.series_flag) q.series_flag = p.series_flag + b0;
     dim3 grid((p.S + TS - 1) / TS, nb);
-    rollout_kernel<<<grid, TS, smem, st>>>(q);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)TS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = p.series_flag ? 1 : 0;     // only when the producer raises per-series flags
+    int s = check_cuda(cudaLaunchKernelEx(&cfg, rollout_kernel, q), "cudaLaunchKernelEx(rollout_kernel)");
+    if (s) return s;
   }
   return check_cuda(cudaGetLastError(), "rollout_kernel");
 }
