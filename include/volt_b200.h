@@ -220,6 +220,15 @@ int volt_rollout_stats(const float* samples, int B, int S, int H, const float* t
 int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t,
                    const float* gh_w, int nq, int B, int n, float inv_n, float* grad_chol, float* rows, void* stream);
 
+/* Batched product C_z (= | -=) A_z B_z^T with fp32-equivalent accuracy on the tensor cores (3xTF32), A_z (M,K), B_z (N,K),
+ * C_z (M,N) row-major; ld*: row strides, *_bstride: floats between batch members (all multiples of 4 floats, pointers
+ * 16-byte aligned).  Replaces the two matrix products behind K^-1 L_S in the GPCV stage's KL term ([GPyTorch] kl_mvn_mvn
+ * inside VariationalELBO, voltron/train_utils.py:46-56, which the reference leaves to torch.matmul) and serves the deferred
+ * trailing updates of the long-series factorisation.  subtract != 0: C -= A B^T (the update is applied in the L2 by a TMA
+ * reduction; C is never loaded by a thread). */
+int volt_gemm_nt(const float* A, long long lda, long long a_bstride, const float* B, long long ldb, long long b_bstride, float* C,
+                 long long ldc, long long c_bstride, int M, int N, int K, int batch, int subtract, void* stream);
+
 /* One torch.optim.Adam step (no weight decay / amsgrad) over a flat parameter buffer: the optimiser of every training
  * loop of the reference (train_utils.py:38-41 lr 0.01; :76-78, :123-125, :236-238 lr 0.01).  step counts from 1; when
  * step_dev is not NULL the count is read from that device float instead (the caller increments it before each launch),

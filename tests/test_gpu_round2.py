@@ -422,3 +422,27 @@ def test_torch_library_ops_match_ctypes_path(vb):
     assert torch.equal(got, want)
     with pytest.raises(RuntimeError):
         ops.vol_cov(x, vol)          # CPU tensors: no CPU implementation is registered
+
+
+# ------------------------------------------------------------------------------------------------ TMA-fed tensor-core product
+@pytest.mark.parametrize("nb,M,N,K", [(1, 128, 128, 16), (1, 128, 256, 64), (3, 400, 400, 400), (2, 399, 399, 399), (1, 1000, 520, 256),
+                                       (5, 64, 48, 33), (1, 2048, 2048, 256)])
+def test_gemm_nt_vs_fp64(vb, nb, M, N, K):
+    """volt_gemm_nt (3xTF32, TMA loads, TMA store / TMA reduction) against an fp64 product: fp32-level accuracy, ragged
+    shapes (partial tiles are clipped by the tensor maps), both the assigning and the subtracting form."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(nb, M, K, generator=g).cuda()
+    B = torch.randn(nb, N, K, generator=g).cuda()
+    want = A.double() @ B.double().transpose(1, 2)
+    got = vb.ops.gemm_nt(A, B)
+    assert got.shape == (nb, M, N)
+    scale = float(want.abs().max())
+    assert float((got.double() - want).abs().max()) < 2e-6 * scale * max(1.0, K ** 0.5 / 8)
+    C0 = torch.randn(nb, M, N, generator=g).cuda()
+    C = C0.clone()
+    vb.ops.gemm_nt(A, B, out=C, subtract=True)
+    assert float((C.double() - (C0.double() - want)).abs().max()) < 2e-6 * scale * max(1.0, K ** 0.5 / 8)
+    # plain TF32 would be ~1e-3 relative: make sure the split is really in effect
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref32 = A @ B.transpose(1, 2)
+    assert float((got - ref32).abs().max()) < 5e-6 * scale * max(1.0, K ** 0.5 / 8)

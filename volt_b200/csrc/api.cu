@@ -715,6 +715,17 @@ int volt_gpcv_rows(const float* chol_var, const float* W, const float* var_mean,
   return launch_gpcv_rows(chol_var, W, var_mean, y, gh_t, gh_w, nq, B, n, inv_n, grad_chol, rows, ST(stream));
 }
 
+int volt_gemm_nt(const float* A, long long lda, long long a_bstride, const float* B, long long ldb, long long b_bstride, float* C,
+                 long long ldc, long long c_bstride, int M, int N, int K, int batch, int subtract, void* stream) {
+  if (batch == 0 || M == 0 || N == 0) return VOLT_OK;
+  VOLT_REQUIRE(A && B && C, "volt_gemm_nt: null pointer");
+  VOLT_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "volt_gemm_nt: bad shape (M=%d N=%d K=%d batch=%d)", M, N, K, batch);
+  VOLT_REQUIRE(lda >= K && ldb >= K && ldc >= N, "volt_gemm_nt: row strides smaller than the rows");
+  VOLT_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+               "volt_gemm_nt: operands must be 16-byte aligned");
+  return launch_gemm_nt(A, lda, a_bstride, B, ldb, b_bstride, C, ldc, c_bstride, M, N, K, batch, subtract ? 1 : 0, 0, 0, ST(stream));
+}
+
 int volt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
                    float beta2, float eps, int step, const float* step_dev, void* stream) {
   VOLT_REQUIRE(param && grad && exp_avg && exp_avg_sq, "volt_adam_step: null pointer");

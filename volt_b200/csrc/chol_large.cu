@@ -595,6 +595,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     cfg.numAttrs = use_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
   };
+  int upd_status = VOLT_OK;
   constexpr int PB = 4;  // blocks per panel: trailing updates outside the panel are deferred and applied with K = 256
   auto update = [&](cudaStream_t s2, int mode, int row_lo, int row_end, int col_lo, int col_hi, int k_lo, int k_hi) {
     const int nrow = (row_end - row_lo + CM - 1) / CM, ncol = (col_hi - col_lo) / NB;
@@ -603,11 +604,29 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     static const int wide_min = [] { const char* e = getenv("VOLT_UPD256_MIN"); return e ? atoi(e) : 1; }();
     const int ncol2w = (col_hi - col_lo + 255) / 256;
     const int live = mode ? nrow * ncol2w : (nrow * ncol2w + 1) / 2 + ncol2w;   // mode 0 keeps the tiles touching the lower triangle
-    if (wide && col_hi - col_lo >= 512 && k_hi - k_lo >= 64 && live >= wide_min) {
+    static const int gemm_min_cols = [] { const char* e = getenv("VOLT_UPD_GEMM_MINCOLS"); return e ? atoi(e) : 256; }();   // c5: 5.94 (256) vs 6.10 ms (512)
+    static const int use_gemm0 = [] { const char* e = getenv("VOLT_UPD_GEMM"); return e ? atoi(e) : 1; }();
+    if (wide && col_hi - col_lo >= (use_gemm0 ? gemm_min_cols : 512) && k_hi - k_lo >= 64 && live >= wide_min) {
       const int ncol2 = ncol2w;
       // the look-ahead part on the side stream leaves a quarter of the SMs to the step kernels of the critical path
       static const int cap_pct = [] { const char* e = getenv("VOLT_UPD256_CAP"); return e ? atoi(e) : 75; }();
       const int cap = (s2 == st) ? sm_count() : max(1, (cap_pct * sm_count()) / 100);
+      // round 2: the TMA-fed product kernel (gemm_nt.cu: operand tiles by cp.async.bulk.tensor, C -= ... as a TMA reduction in
+      // the L2).  VOLT_UPD_GEMM=0: the register-staged 128 x 256 tile kernel of round 1 (A/B timing).
+      static const int use_gemm = [] { const char* e = getenv("VOLT_UPD_GEMM"); return e ? atoi(e) : 1; }();
+      if (use_gemm) {
+        const size_t ld = (size_t)p.Tp;
+        int rc;
+        if (mode == 0)
+          rc = launch_gemm_nt(p.W + (size_t)row_lo * ld + k_lo, (long long)ld, 0, p.W + (size_t)col_lo * ld + k_lo, (long long)ld, 0,
+                              p.W + (size_t)row_lo * ld + col_lo, (long long)ld, 0, row_end - row_lo, col_hi - col_lo, k_hi - k_lo, 1, 1,
+                              row_lo == col_lo ? 1 : 0, cap, s2);
+        else
+          rc = launch_gemm_nt(p.Ut + k_lo, (long long)ld, 0, p.W + (size_t)col_lo * ld + k_lo, (long long)ld, 0, p.Ut + col_lo,
+                              (long long)ld, 0, row_end, col_hi - col_lo, k_hi - k_lo, 1, 1, 0, cap, s2);
+        if (rc) upd_status = rc;
+        return;
+      }
       large_update256_kernel<<<min(ncol2 * nrow, cap), NT, UPDATE2_SMEM, s2>>>(p, mode, row_lo, row_end, col_lo, col_hi, k_lo, k_hi);
       return;
     }
@@ -668,6 +687,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
     s = join(rest_pending);
     if (s) return s;
   }
+  if (upd_status) return upd_status;
   large_finish_kernel<<<1, 256, 0, st>>>(p, jit_used, mp.scalars + (size_t)b * NSCALARS,
                                          (mp.alpha && mp.do_inverse) ? mp.alpha + (size_t)b * mp.T : nullptr,
                                          mp.info ? mp.info + b : nullptr);

@@ -357,6 +357,41 @@ def mvn_sample(mean, cov, eps, jitter=1e-6, exp_out=False):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ tensor-core product
+def gemm_nt(A, B, out=None, subtract=False):
+    """C (= | -=) A @ B^T per batch member on the tensor cores with fp32-equivalent accuracy (volt_gemm_nt: 3xTF32, TMA in /
+    TMA out).  A (..., M, K), B (..., N, K) -> (..., M, N).  Rows are padded to a multiple of 4 floats when needed (the
+    tensor maps want 16-byte row strides)."""
+    dev = _dev()
+    M, K = A.shape[-2:]
+    N = B.shape[-2]
+    lead = A.shape[:-2]
+    Ad, Bd = _f32(A, dev).reshape(-1, M, K), _f32(B, dev).reshape(-1, N, K)
+    nb = Ad.shape[0]
+    if Bd.shape[0] != nb:
+        raise ValueError("gemm_nt: A and B need the same batch shape")
+
+    def pad4(t):
+        k = t.shape[-1]
+        return t if k % 4 == 0 else torch.nn.functional.pad(t, (0, 4 - k % 4)).contiguous()
+
+    Ad, Bd = pad4(Ad), pad4(Bd)
+    ldc = (N + 3) // 4 * 4
+    if out is None:
+        if subtract:
+            raise ValueError("gemm_nt: subtract needs `out`")
+        Cp = _empty((nb, M, ldc), dev)
+    else:
+        Cp = pad4(_f32(out, dev).reshape(nb, M, N))
+    _lib.check(_lib.load().volt_gemm_nt(_ptr(Ad), Ad.shape[-1], M * Ad.shape[-1], _ptr(Bd), Bd.shape[-1], N * Bd.shape[-1], _ptr(Cp),
+                                        ldc, M * ldc, M, N, K, nb, int(subtract), _stream()), "volt_gemm_nt")
+    C = Cp[..., :N]
+    if out is not None and C.data_ptr() != out.data_ptr():
+        out.copy_(C.reshape(out.shape))
+        return out
+    return C.reshape(*lead, M, N)
+
+
 # ------------------------------------------------------------------------------------------------ rollout
 def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0.5, mr_latent=None, resid_given=None,
             mean_test=None, theta=None, latent=None, joint=False, jitter=1e-4, seed=0, vol_mode=VOL_SIGMA, check=True):
