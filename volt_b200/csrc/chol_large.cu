@@ -37,6 +37,8 @@ struct LargeParams {
   int trp_ld;
   float* origd;        // (Tp) original diagonal of A (pivot failure predicate)
   int* flag;           // first failing pivot index, -1 = none
+  int* step_flag;      // (nb) step_flag[j] == epoch: the diagonal block of step j of this attempt has been published
+  int epoch;
 };
 
 __device__ __forceinline__ float gen_large(const LargeParams& p, int i, int j) {
@@ -134,51 +136,53 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
   const uint32_t t_lane = (uint32_t)(32 * (warp & 3)) << 16;
   // Inside a 256-column panel the updates are LEFT-looking: block column j receives the contributions of the panel's
   // earlier block columns [kp, R0) right here (K <= 192), so no separate update launch sits between two steps.
-  {
-    float u[32];
-    const bool have = gemm_tc<false>(c, p.W, ld, R0, p.Tp, R0, kp, R0, nullptr);   // rows R0.. (the diagonal block is rows < 64)
-    if (have) {
-      tmem_ld32(c.tmem + t_lane + (uint32_t)c0, u);
-      tc_fence_before();
-    } else {
+  // Round 2: the roles are split by CTA.  CTA 0 forms, factors and inverts the 64 x 64 diagonal block and publishes
+  // Linv_jj / z_j / log-det / the failure flag behind a per-step flag; CTAs 1.. apply the earlier block columns to their 128
+  // rows FIRST (that product does not need the diagonal block), then wait for the flag, then solve.  Before, every CTA
+  // factored the block itself and only then started its own product: 26.6 -> 21 us per step at T = 8192.
+  if (blockIdx.x == 0) {
+    {
+      float u[32];
+      const bool have = gemm_tc<false>(c, p.W, ld, R0, p.Tp, R0, kp, R0, nullptr);   // rows R0.. (the diagonal block is rows < 64)
+      if (have) {
+        tmem_ld32(c.tmem + t_lane + (uint32_t)c0, u);
+        tc_fence_before();
+      } else {
 #pragma unroll
-      for (int q = 0; q < 32; ++q) u[q] = 0.f;
-    }
-    if (row < NB) {
-      const float4* src = reinterpret_cast<const float4*>(p.W + (size_t)(R0 + row) * ld + R0 + c0);
+        for (int q = 0; q < 32; ++q) u[q] = 0.f;
+      }
+      if (row < NB) {
+        const float4* src = reinterpret_cast<const float4*>(p.W + (size_t)(R0 + row) * ld + R0 + c0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = src[q];
-        *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) =
-            make_float4(v.x - u[4 * q], v.y - u[4 * q + 1], v.z - u[4 * q + 2], v.w - u[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = src[q];
+          *reinterpret_cast<float4*>(c.Ct + row * CLD + c0 + 4 * q) =
+              make_float4(v.x - u[4 * q], v.y - u[4 * q + 1], v.z - u[4 * q + 2], v.w - u[4 * q + 3]);
+        }
       }
     }
-  }
-  if (tid == 0) *c.flag = -1;
-  if (tid < NB) { c.tmp[tid] = p.origd[R0 + tid]; c.tmp[NB + tid] = p.z[R0 + tid]; }
-  __syncthreads();
-  diag64_block_v2<CLD>(c.Ct, sh.LiT, sh.tmpbuf, c.diagl, c.tmp, c.flag, R0);
-  __syncthreads();
-  float zj = 0.f;
-  if (tid < NB)
-    for (int k = 0; k <= tid; ++k) zj = fmaf(sh.LiT[k * CLD + tid], c.tmp[NB + k], zj);
-  __syncthreads();
-  if (tid < NB) c.tmp[tid] = zj;                       // z_j = Linv_jj r_j (origd is dead)
-  stage_linv_from_lit(c, sh.LiT);
-  if (blockIdx.x == 0) {
+    if (tid == 0) *c.flag = -1;
+    if (tid < NB) { c.tmp[tid] = p.origd[R0 + tid]; c.tmp[NB + tid] = p.z[R0 + tid]; }
+    wsync();
+    diag64_block_v2<CLD>(c.Ct, sh.LiT, sh.tmpbuf, c.diagl, c.tmp, c.flag, R0);
+    wsync();
+    float zj = 0.f;
+    if (tid < NB)
+      for (int k = 0; k <= tid; ++k) zj = fmaf(sh.LiT[k * CLD + tid], c.tmp[NB + k], zj);
     float* dj = p.dinv + (size_t)j * NB * NB;
     for (int idx = tid; idx < NB * NB; idx += NT) dj[idx] = sh.LiT[(idx >> 6) * CLD + (idx & 63)];
-    if (tid < NB) p.zf[R0 + tid] = zj;
+    if (tid < NB) p.zf[R0 + tid] = zj;               // z_j = Linv_jj r_j
     float lg = (tid < NB && R0 + tid < p.T) ? logf(c.diagl[tid]) : 0.f;
     lg = block_sum(lg, c.red);
     if (tid == 0) {
       p.acc[0] += lg;                                  // one writer per step, launches are stream-ordered
       if (*c.flag >= 0 && *p.flag < 0) *p.flag = *c.flag;
     }
-  }
-  __syncthreads();                                     // LiT / tmpbuf (aliasing the stage region) are dead from here on
-  const int r_base = R0 + NB + CM * blockIdx.x, row_end = p.Tp;
-  if (r_base < row_end) {
+    __threadfence();
+    wsync();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.step_flag + j), "r"(p.epoch) : "memory");
+  } else {
+    const int r_base = R0 + NB + CM * ((int)blockIdx.x - 1), row_end = p.Tp;
     const int gr = r_base + row;
     float s[32], o[32];
     const bool have = gemm_tc<false>(c, p.W, ld, r_base, row_end, R0, kp, R0, nullptr);
@@ -200,6 +204,20 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
 #pragma unroll
       for (int q = 0; q < 32; ++q) s[q] = 0.f;
     }
+    // the diagonal block of this step (CTA 0 of this launch; every CTA of the launch is resident: the grid is at most
+    // Tp / 128 + 1 CTAs at two per SM)
+    if (tid == 0) {
+      int f = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.step_flag + j) : "memory");
+        if (f == p.epoch) break;
+        __nanosleep(64);
+      }
+    }
+    wsync();
+    stage_linv_from_dinv(c, p.dinv + (size_t)j * NB * NB);
+    if (tid < NB) c.tmp[tid] = p.zf[R0 + tid];
+    wsync();
     trsm_tc(c, s, o, row, half_id);
     {
       const int g0 = r_base + 32 * (warp & 3);
@@ -209,7 +227,7 @@ __global__ void __launch_bounds__(NT, 2) large_diagpanel_kernel(LargeParams p, i
 #pragma unroll
     for (int q = 0; q < 32; ++q) dot = fmaf(o[q], c.tmp[c0 + q], dot);
     if (half_id) c.tmp[NB + row] = dot;                // the two column halves of a row are combined in a fixed order
-    __syncthreads();
+    wsync();
     if (half_id == 0 && gr < row_end) p.z[gr] -= dot + c.tmp[NB + row];
   }
   cta_teardown(sh);
@@ -533,7 +551,7 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   s = get_workspace(tp2 * sizeof(float), &u, 10, st);
   if (s) return s;
   p.trp_ld = (p.Tp + CM - 1) / CM + 1;
-  const size_t aux_fl = (size_t)p.nb * NB * NB + 4 * (size_t)p.Tp + 16 + (size_t)p.nb * p.trp_ld;
+  const size_t aux_fl = (size_t)p.nb * NB * NB + 4 * (size_t)p.Tp + 16 + (size_t)p.nb * p.trp_ld + (size_t)p.nb;
   s = get_workspace(aux_fl * sizeof(float), &aux, 11, st);
   if (s) return s;
   p.W = (float*)w;
@@ -546,6 +564,8 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   p.acc = p.zf + p.Tp;
   p.flag = reinterpret_cast<int*>(p.acc + 4);
   p.trp = p.acc + 16;
+  p.step_flag = reinterpret_cast<int*>(p.trp + (size_t)p.nb * p.trp_ld);
+  VOLT_CUDA(cudaMemsetAsync(p.step_flag, 0, (size_t)p.nb * sizeof(int), st));
   if (mp.kind == KIND_VOL) p.V = mp.V + (size_t)b * mp.T;
   else if (mp.kind == KIND_BM) { p.V = mp.x; }
   else { p.dense = mp.dense + (size_t)b * mp.dense_bstride; p.ldd = mp.ldd; }
@@ -659,13 +679,14 @@ int launch_mll_large(const MllParams& mp, int b, cudaStream_t st) {
   float jit_used = 0.f;
   for (int attempt = 0;; ++attempt) {
     p.dadd = dadd0 + jit_used;
+    p.epoch = attempt + 1;
     VOLT_CUDA(cudaMemsetAsync(p.Ut, 0, tp2 * sizeof(float), st));
     large_build_kernel<<<p.Tp, 256, 0, st>>>(p);
     bool rest_pending = false;
     for (int j = 0; j < p.nb; ++j) {
       const int R0 = j * NB, panel_end = min(p.Tp, (j / PB + 1) * PB * NB);
       const int rows = p.Tp - (R0 + NB);
-      VOLT_CUDA(launch_step(large_diagpanel_kernel, max(1, (rows + CM - 1) / CM), p, j, (j / PB) * PB * NB));
+      VOLT_CUDA(launch_step(large_diagpanel_kernel, 1 + max(0, (rows + CM - 1) / CM), p, j, (j / PB) * PB * NB));
       if (rows > 0 && R0 + NB == panel_end) { s = deferred(0, panel_end, rest_pending); if (s) return s; }
     }
     s = join(rest_pending);
