@@ -3,11 +3,12 @@ path.  B independent series are trained at once, device
 
   * the T^3 pieces per iteration -- factorisation of K = vol min(x,x') + 1e-3 I, logdet K, tr K^-1, K^-1 (c - m) and the
     inverse factor (L^-1)^T -- come from ONE launch of the batched tensor-core MLL kernel (`volt_mll_grad_bm_inv`);
-  * W = K^-1 L_S = U (U^T L_S) is two plain library GEMMs (torch.bmm -> cuBLAS, fp32);
+  * W = K^-1 L_S = U (U^T L_S) is two launches of this library's TMA-fed tensor-core product (`volt_gemm_nt`, 3xTF32);
   * `volt_gpcv_rows` turns them into the per-point Gauss-Hermite likelihood terms, the loss pieces and the gradient of the
     T x T variational factor; `volt_adam_step` is the optimiser over the flat parameter buffer.
 
-[GPyTorch slice restated from memory, see oracle.volt_oracle: parity with the reference is unpinned for this stage.]
+[GPyTorch slice restated from memory, see oracle.volt_oracle; pinned in round 2 against the loss trace real GPyTorch printed
+in the reference's example.ipynb (tests/notebook_data.py).]
 """
 import math
 
@@ -17,6 +18,9 @@ import torch
 from . import _lib, ops
 from ._lib import S_INVQUAD, S_LOGDET, S_TRINV
 
+import os
+
+_AB_BMM = os.environ.get("VOLT_GPCV_BMM") == "1"
 PRIOR_JITTER = 1e-3      # [GPyTorch] UnwhitenedVariationalStrategy.prior_distribution: add_jitter() default
 NUM_GH = 75              # train_utils.py:52
 NUM_LIK_SAMPLES = 10     # [GPyTorch] settings.num_likelihood_samples (Likelihood.marginal)
@@ -101,6 +105,8 @@ def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=F
     jit = torch.full((B,), PRIOR_JITTER, device=dev)
     rows = torch.empty(B, n, 6, device=dev)
     U = torch.empty(B, n, n, device=dev)
+    Qt = torch.empty(B, n, n, device=dev)
+    W = torch.empty(B, n, n, device=dev)
     sc = torch.empty(B, 16, device=dev)
     alpha = torch.empty(B, n, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
@@ -119,7 +125,14 @@ def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=F
         # alpha = K^-1 d and the inverse factor U = (L^-1)^T
         _lib.check(lib.volt_mll_grad_bm_inv(x.data_ptr(), vol.data_ptr(), 1, d.data_ptr(), jit.data_ptr(), 1, B, n, 1e-6, 3,
                                             sc.data_ptr(), alpha.data_ptr(), info.data_ptr(), U.data_ptr(), st), "volt_mll_grad_bm_inv")
-        W = torch.bmm(U, torch.bmm(U.transpose(1, 2), torch.tril(cv)))              # K^-1 L_S: two library GEMMs
+        # K^-1 L_S = U (U^T L_S) as two tensor-core products of this library (volt_gemm_nt: 3xTF32, TMA-fed; round 1 used
+        # torch.bmm / cuBLAS).  The kernel contracts over the last index of both operands, so the first product is formed
+        # transposed: Q^T = L_S^T X^T with X = U^T, then W = U Q.
+        if _AB_BMM:      # developer A/B switch (VOLT_GPCV_BMM=1): the round-1 library GEMMs
+            W.copy_(torch.bmm(U, torch.bmm(U.transpose(1, 2), torch.tril(cv))))
+        else:
+            ops.gemm_nt(torch.tril(cv).transpose(1, 2), U.transpose(1, 2), out=Qt)
+            ops.gemm_nt(U, Qt, out=W)
         _lib.check(lib.volt_gpcv_rows(cv.data_ptr(), W.data_ptr(), vm.data_ptr(), y.data_ptr(), gh_t.data_ptr(), gh_w.data_ptr(),
                                       NUM_GH, B, n, inv_n, g_cv.data_ptr(), rows.data_ptr(), st), "volt_gpcv_rows")
         rs = rows.sum(1)                                                           # (B,6)
@@ -149,14 +162,20 @@ def learn_gpcv(train_x, train_y, train_iters=1000, lr=0.01, eps=None, printing=F
         after(done)
     graph = None
     if done < train_iters and use_graph:
+        prev_stream = torch.cuda.current_stream()
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 iteration()
             graph = g
-        except Exception:  # noqa: BLE001  (capture unsupported: stay eager on the GPU)
+        except Exception as exc:  # noqa: BLE001  (capture refused: stay eager on the GPU, and say so)
+            import warnings
+
             graph = None
+            torch.cuda.set_stream(prev_stream)      # a failed capture_end leaves the side stream current
+            torch.cuda.synchronize()
+            warnings.warn(f"volt_b200.gpcv: CUDA-graph capture of the Adam iteration failed ({exc}); running eagerly", RuntimeWarning)
     while done < train_iters:
         if graph is not None:
             graph.replay()
