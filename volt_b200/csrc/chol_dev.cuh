@@ -299,43 +299,68 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
   float* WT = XT + 16 * XT_LD;                   // 48 x 20: per inverse block (16 x 20), WT[c][k] = W[k][c]
   const int ti = tid & 7, tj = (tid >> 3) & 7, tg = tid >> 6;   // 2 x 2 tile owner: rows {ti, ti+8}, cols {tj, tj+8}, group tg
   int failc = -1;
-  for (int p = 0; p < 4; ++p) {
+  // Look-ahead (round 2): the 16 x 16 pivot block of panel p + 1 only needs panel p's update of THAT block, so warp 0 applies
+  // it itself right after the panel solve and goes on factoring while warps 1-7 write the panel back and apply the rest of the
+  // trailing update.  The one-warp pivot chain (4 x 3.4 k cycles) then hides the trailing updates instead of alternating with them.
+  if (warp == 0) pivot16_warp<RLD>(D, LiT, I16, diagl, origd, 0, lane, failc);
+  else {
+    for (int i = tid - 32; i < 64 * 64; i += NT - 32) {
+      const int k = i >> 6, cc = i & 63;
+      if ((k >> 4) != (cc >> 4)) LiT[k * RLD + cc] = 0.f;   // diagonal 16-blocks are written by the pivot warps
+    }
+  }
+  DTICK(0);
+  for (int p = 0; p < 3; ++p) {
     const int o = 16 * p;
     const int R = 48 - o;                        // rows below the pivot block
-    // ---- P1: pivot block (warp 0); the other warps clear LiT once
-    if (warp == 0) pivot16_warp<RLD>(D, LiT, I16 + p * 16 * I16_LD, diagl, origd, o, lane, failc);
-    else if (p == 0) {
-      for (int i = tid - 32; i < 64 * 64; i += NT - 32) {
-        const int k = i >> 6, cc = i & 63;
-        if ((k >> 4) != (cc >> 4)) LiT[k * RLD + cc] = 0.f;   // diagonal 16-blocks are written by the pivot warps
-      }
-    }
-    DTICK(0);
-    wsync();
+    wsync();                                     // pivot block p factored and inverted; trailing update of panel p - 1 complete
     DTICK(1);
-    if (R > 0) {
-      // ---- P2: panel solve X = S_panel Linv16^T, 16-row groups x (2 x 2 tiles); result kept transposed in XT
-      if (tid < R * 4) {
-        const float* a0 = D + (o + 16 + 16 * tg + ti) * RLD + o;
-        const float* b0 = I16 + p * 16 * I16_LD + tj * I16_LD;
-        float x00, x01, x10, x11;
-        dot2x2(a0, a0 + 8 * RLD, b0, b0 + 8 * I16_LD, 16, x00, x01, x10, x11);
-        const int r0 = 16 * tg + ti;
-        XT[tj * XT_LD + r0] = x00; XT[(tj + 8) * XT_LD + r0] = x01;
-        XT[tj * XT_LD + r0 + 8] = x10; XT[(tj + 8) * XT_LD + r0 + 8] = x11;
+    // ---- P2: panel solve X = S_panel Linv16^T, 16-row groups x (2 x 2 tiles); result kept transposed in XT
+    if (tid < R * 4) {
+      const float* a0 = D + (o + 16 + 16 * tg + ti) * RLD + o;
+      const float* b0 = I16 + p * 16 * I16_LD + tj * I16_LD;
+      float x00, x01, x10, x11;
+      dot2x2(a0, a0 + 8 * RLD, b0, b0 + 8 * I16_LD, 16, x00, x01, x10, x11);
+      const int r0 = 16 * tg + ti;
+      XT[tj * XT_LD + r0] = x00; XT[(tj + 8) * XT_LD + r0] = x01;
+      XT[tj * XT_LD + r0 + 8] = x10; XT[(tj + 8) * XT_LD + r0 + 8] = x11;
+    }
+    wsync();
+    DTICK(2);
+    if (warp == 0) {
+      // next pivot block: D[o+16+i][o+16+j] -= X[i] . X[j], i, j < 16 (lane: row i, eight columns), then factor it
+      const int i = lane & 15, jh = 8 * (lane >> 4);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < 16; ++t) {
+        const float a = XT[t * XT_LD + i];
+        const float4 b0 = *reinterpret_cast<const float4*>(XT + t * XT_LD + jh), b1 = *reinterpret_cast<const float4*>(XT + t * XT_LD + jh + 4);
+        acc[0] = fmaf(a, b0.x, acc[0]); acc[1] = fmaf(a, b0.y, acc[1]); acc[2] = fmaf(a, b0.z, acc[2]); acc[3] = fmaf(a, b0.w, acc[3]);
+        acc[4] = fmaf(a, b1.x, acc[4]); acc[5] = fmaf(a, b1.y, acc[5]); acc[6] = fmaf(a, b1.z, acc[6]); acc[7] = fmaf(a, b1.w, acc[7]);
       }
-      wsync();
-      DTICK(2);
-      // ---- P3: write the panel back (row fastest) and apply the trailing update D[r][c] -= X[r].X[c] in 4 x 4 tiles
-      //      that touch the lower triangle (the strictly-upper entries a diagonal tile also updates are never read)
-      if (tid < R * 4) {
-        const int rr = (tid & 15) + 16 * (tid >> 6), cq = ((tid >> 4) & 3) * 4;
+      float4* dst = reinterpret_cast<float4*>(D + (o + 16 + i) * RLD + o + 16 + jh);
+      float4 v0 = dst[0], v1 = dst[1];
+      v0.x -= acc[0]; v0.y -= acc[1]; v0.z -= acc[2]; v0.w -= acc[3];
+      v1.x -= acc[4]; v1.y -= acc[5]; v1.z -= acc[6]; v1.w -= acc[7];
+      dst[0] = v0; dst[1] = v1;
+      __syncwarp();
+      pivot16_warp<RLD>(D, LiT, I16 + (p + 1) * 16 * I16_LD, diagl, origd, o + 16, lane, failc);
+    } else {
+      // ---- P3 (warps 1-7): write the panel back (row fastest) and apply the rest of the trailing update
+      //      D[r][c] -= X[r].X[c] in 4 x 4 tiles that touch the lower triangle (the strictly-upper entries a diagonal tile also
+      //      updates are never read); tiles 0-9 are the next pivot block (warp 0)
+      const int t = tid - 32;
+      if (t < R * 4) {
+        const int rr = (t & 15) + 16 * (t >> 6), cq = ((t >> 4) & 3) * 4;
         *reinterpret_cast<float4*>(D + (o + 16 + rr) * RLD + o + cq) =
             make_float4(XT[cq * XT_LD + rr], XT[(cq + 1) * XT_LD + rr], XT[(cq + 2) * XT_LD + rr], XT[(cq + 3) * XT_LD + rr]);
       }
       const int nr = R >> 2, ntile = nr * (nr + 1) / 2;
-      if (tid < ntile) {
-        int ri = 0, ci = tid;
+      const int q = t + 10;
+      if (q < ntile) {
+        int ri = 0, ci = q;
         while (ci > ri) { ci -= ri + 1; ++ri; }
         float acc[4][4];
 #pragma unroll
@@ -343,9 +368,9 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
-        for (int t = 0; t < 16; ++t) {
-          const float4 a4 = *reinterpret_cast<const float4*>(XT + t * XT_LD + 4 * ri);
-          const float4 b4 = *reinterpret_cast<const float4*>(XT + t * XT_LD + 4 * ci);
+        for (int tt = 0; tt < 16; ++tt) {
+          const float4 a4 = *reinterpret_cast<const float4*>(XT + tt * XT_LD + 4 * ri);
+          const float4 b4 = *reinterpret_cast<const float4*>(XT + tt * XT_LD + 4 * ci);
           const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -360,10 +385,10 @@ __device__ void diag64_block_v2(float* D, float* LiT, float* scratch, float* dia
           *dst = v;
         }
       }
-      wsync();
-      DTICK(3);
     }
+    DTICK(3);
   }
+  wsync();
   if (tid == 0 && failc >= 0 && *flag < 0) *flag = col0 + failc;
   // ---- inverse: off-diagonal 16-blocks by block distance d = pb - qb.
   //   W[r][c] = sum_{k in [16 qb, 16 pb)} L[16 pb + r][k] Linv[k][16 qb + c]  (= D row . LiT row, both contiguous)
