@@ -317,9 +317,10 @@ def main():
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # K timed steps.  The all-reduce of step s runs on a side stream under step s + 1; the end event of a step is
-    # recorded after the current stream has waited for the PREVIOUS step's collective (the last step waits for its own),
-    # so every collective completes inside a timed region.
+    # K timed steps.  The cross-rank sum of step s completes under step s + 1 (pushed to the peers by the kernel of step s
+    # and added up at the end of the kernel of step s + 1; with VOLT_LOSS_EXCHANGE=nccl an all-reduce on a side stream);
+    # the end event of a step is recorded after the current stream has waited for the PREVIOUS step's total (the last
+    # step waits for its own), so every exchange completes inside a timed region.
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = _lib.launch_count()
     prev = None
@@ -444,7 +445,13 @@ def main():
             print(f"[bench] stock-torch GPU baseline skipped: {exc}", file=sys.stderr)
 
     t = torch.tensor([total_ms, e2e_t * 1e3, kern_ms, roll_ms], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        # every rank's own numbers next to the max: the spread between GPUs of one box is what weak scaling loses here
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = dict(ms_per_step=[round(float(a[0]) / args.steps, 4) for a in allt],
+                        kernel_ms=[round(float(a[2]), 4) for a in allt])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, kern_ms, roll_ms = (float(v) for v in t)
     value = B * world * args.steps / (total_ms * 1e-3)
@@ -473,6 +480,7 @@ def main():
                  d2h_bytes_per_step=int(B * 16 * 4 + B * 4 + (4 if world > 1 else 0)),
                  collective=("loss all-reduce inside the timed step" if world > 1 else "none (one rank)")),
         gpu_launches=int(launches),
+        **({"per_rank": per_rank, "loss_exchange": type(out["loss"]).__name__} if world > 1 else {}),
         clocks=clocks,
         peaks=dict(hbm_gbs=pk["hbm"], bf16_tflops_sustained=pk["tf"], source=pk["source"], tf32_tflops=tf32),
         roofline=dict(bound="hbm", achieved=ach_gbs, peak=pk["hbm"], unit="GB/s", frac=ach_gbs / pk["hbm"], traffic=traffic,

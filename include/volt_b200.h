@@ -132,6 +132,27 @@ int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int v
                           int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
                           float* loss_out, void* stream);
 
+/* volt_mll_grad_vol_raw for a series-sharded job (one process per GPU, each rank holds B of the series): the compute step and
+ * the exchange of the loss in ONE kernel, no collective launch.  Every rank owns an exchange buffer of ring*world 64-bit
+ * slots in peer-mapped memory; after the fixed-order sum, the kernel's last CTA stores {seq, -sum_b MLL_b} (one 64-bit
+ * word) into slot [seq % ring][rank] of EVERY rank's buffer over NVLink, and -- when prev_totals is given -- adds up step
+ * seq-1's slots of its own buffer (they arrived while this step ran), in rank order so every rank gets the same bits:
+ * prev_totals[(seq-1) % ring] = total loss of step seq-1.
+ *   peer_slot_ptrs: DEVICE array of `world` pointers, entry r = rank r's buffer mapped into this process
+ *                   (torch.distributed._symmetric_memory buffer_ptrs_dev, or cudaIpc / cuMem mappings); slots start zeroed.
+ *   local_slots:    this rank's own buffer (needed with prev_totals).   prev_totals: ring floats or NULL (first step).
+ *   seq:            step number, the same on every rank, 1, 2, 3, ...; ring >= 2 and no rank may run more than ring-1
+ *                   steps ahead of another (prev_totals bounds it to 1).
+ * Replaces the scalar the reference builds from the loss on one process (voltron/train_utils.py:249-250); the reference
+ * has no multi-process path.  An empty shard (B = 0) pushes 0.
+ * volt_loss_gather: total of step seq from this rank's slots (for the newest step, which no later kernel has summed yet);
+ * waits on the device, bounded (~2 s, then NaN), for slots that have not arrived.  out: 1 float. */
+int volt_mll_step_sharded(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
+                          int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                          float* loss_out, const void* peer_slot_ptrs, const void* local_slots, float* prev_totals, int world, int rank,
+                          int ring, unsigned int seq, void* stream);
+int volt_loss_gather(const void* local_slots, int world, int ring, unsigned int seq, float* out, void* stream);
+
 /* Same for the vol model BMGP (A = scale_b * min(x_i, x_j) + noise_b I)  -- voltron/train_utils.py:86-90,
  * voltron/models/BMGP.py:20-28.  x (T) shared grid. */
 int volt_mll_grad_bm(const float* x, const float* scale, int scale_stride, const float* resid, const float* noise,

@@ -446,3 +446,84 @@ def test_gemm_nt_vs_fp64(vb, nb, M, N, K):
     torch.backends.cuda.matmul.allow_tf32 = False
     ref32 = A @ B.transpose(1, 2)
     assert float((got - ref32).abs().max()) < 5e-6 * scale * max(1.0, K ** 0.5 / 8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# series-sharded step: loss partials pushed into every rank's slots by the kernel (volt_mll_step_sharded / volt_loss_gather)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T", [(24, 400), (3, 100), (2, 1600)])   # tensor-core step kernel, SIMT fallback, large path
+def test_sharded_step_pushes_partial_to_every_rank(B, T):
+    """Two 'ranks' emulated on one device: each rank's buffer is an ordinary allocation, both are listed in the peer table.
+    After rank 0 and rank 1 have run step `seq`, each buffer holds {seq, partial_r} in slot [seq % ring][r], and the gather
+    returns partial_0 + partial_1 (rank order) from either buffer; outputs equal volt_mll_grad_vol_raw's."""
+    from volt_b200 import _lib, batched, ops
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    world, ring = 2, 4
+    bufs = [torch.zeros(ring * world, dtype=torch.int64, device=dev) for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    x, vol, logy = batched.synth_series(2 * B, T, 1.0 / 252)
+    xd = x.to(dev)
+    resid_all = ops.ma_mean("ewma", logy.to(dev), 20, want_resid=True)[1]
+    totals = [torch.full((ring,), float("nan"), device=dev) for _ in range(world)]
+    last = None
+    for seq in (1, 2, 3, 4, 5, 6):                                            # 5, 6 reuse the rows of 1, 2
+        partials = []
+        for r in range(world):
+            vd, rd = vol.to(dev)[r * B:(r + 1) * B], resid_all[r * B:(r + 1) * B]
+            raw = torch.full((B,), -3.0 + 0.1 * seq, device=dev)
+            ref = ops.mll_step("vol", xd, vd, rd, raw, check=True)
+            got = ops.mll_step("vol", xd, vd, rd, raw, check=True,
+                               exchange=(table.data_ptr(), bufs[r].data_ptr(), totals[r] if seq > 1 else None, world, r, ring, seq))
+            assert torch.equal(got["scalars"][:, :12], ref["scalars"][:, :12]) and torch.equal(got["alpha"], ref["alpha"])
+            assert torch.equal(got["loss"], ref["loss"])
+            partials.append(ref["loss"].reshape(()))
+        torch.cuda.synchronize()
+        for b in bufs:
+            row = b[(seq % ring) * world:(seq % ring + 1) * world].cpu()
+            assert [int(v) >> 32 for v in row] == [seq, seq]
+            out = torch.empty(1, device=dev)
+            _lib.check(lib.volt_loss_gather(b.data_ptr(), world, ring, seq, out.data_ptr(), st), "volt_loss_gather")
+            assert torch.equal(out.reshape(()), partials[0] + partials[1])
+        if last is not None:                                                  # the kernels of this step summed the previous one
+            for r in range(world):
+                assert torch.equal(totals[r][(seq - 1) % ring], last)
+        last = partials[0] + partials[1]
+
+
+@pytest.mark.gpu
+def test_sharded_step_empty_shard_and_bad_description():
+    from volt_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    buf = torch.zeros(4, dtype=torch.int64, device=dev)
+    table = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=dev)
+    loss = torch.full((1,), 7.0, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.volt_mll_step_sharded(None, 0, None, 1, None, None, 1, 0, 400, 1e-6, 3, None, None, None, loss.data_ptr(),
+                                   table.data_ptr(), buf.data_ptr(), None, 1, 0, 4, 9, st)
+    assert rc == 0
+    out = torch.empty(1, device=dev)
+    assert lib.volt_loss_gather(buf.data_ptr(), 1, 4, 9, out.data_ptr(), st) == 0
+    torch.cuda.synchronize()
+    assert float(loss) == 0.0 and float(out) == 0.0 and int(buf[1]) >> 32 == 9
+    assert lib.volt_mll_step_sharded(None, 0, None, 1, None, None, 1, 0, 400, 1e-6, 3, None, None, None, loss.data_ptr(),
+                                     table.data_ptr(), buf.data_ptr(), None, 2, 2, 4, 9, st) != 0   # rank outside [0, world)
+    assert b"exchange" in lib.volt_last_error()
+
+
+@pytest.mark.gpu
+def test_loss_exchange_two_gpus():
+    """The real thing on two GPUs (skipped on a one-GPU box): tools/exchange_check.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "exchange_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "EXCHANGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

@@ -5,7 +5,7 @@ fallback: if the library is missing, or the current device is not an sm_100 GPU,
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_uint, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # VOLT_B200_LIB: developer override used by tools/ab.sh to time experimental builds of the same ABI side by side
@@ -33,6 +33,9 @@ _SIGS = {
                                   c_void_p]),
     "volt_mll_grad_vol_raw": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp,
                                       c_void_p]),
+    "volt_mll_step_sharded": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp,
+                                      c_void_p, c_void_p, _fp, c_int, c_int, c_int, c_uint, c_void_p]),
+    "volt_loss_gather": (c_int, [c_void_p, c_int, c_int, c_uint, _fp, c_void_p]),
     "volt_mll_grad_bm": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_bm_inv": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_dense": (c_int, [_fp, c_longlong, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp,

@@ -2,14 +2,18 @@
 SURVEY.md section 0) and the series-sharded multi-GPU layout.
 
 One process per GPU (torch.distributed, NCCL).  Series are independent, so each rank owns a contiguous block of
-B / world series and the only data-path collective is one all-reduce of the scalar loss per MLL evaluation;
+B / world series and the only data-path exchange is the sum of the scalar loss per MLL evaluation -- pushed to the peers
+by the MLL kernel itself (LossExchange), an NCCL all-reduce on a side stream where peer memory is unavailable;
 rollouts need none."""
 import math
+import os
+import warnings
+import weakref
 
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from ._lib import S_DRAW, S_MLL
 
 
@@ -91,6 +95,105 @@ def _async_loss_all_reduce(partial):
     return PendingLoss(buf.reshape(()), done)
 
 
+class _ExchangedLoss(PendingLoss):
+    """Loss of a step whose partials were pushed to every rank by the MLL kernel itself (LossExchange)."""
+
+    def __init__(self, exchange, seq):
+        self._ex, self._seq, self._t, self._ev = exchange, seq, None, None
+
+    def wait(self):
+        if self._t is None:
+            self._t = self._ex._total(self)
+        if self._ev is not None:                       # summed by the next step's kernel: order after that launch
+            torch.cuda.current_stream().wait_event(self._ev)
+            self._ev = None
+        return self._t
+
+
+class LossExchange:
+    """The cross-rank sum of the step loss WITHOUT a collective launch: every rank owns a symmetric-memory
+    buffer of RING x world 64-bit slots; the MLL kernel's last CTA stores {step number, partial} into slot
+    [step % RING][rank] of every rank's buffer over NVLink and adds up the previous step's slots of its own buffer
+    (volt_mll_step_sharded), so in a training loop the total of step s is simply there once step s + 1 has run; only the
+    newest step needs a tiny kernel that waits for its `world` slots (volt_loss_gather).  A separate NCCL kernel cannot
+    overlap the next step here -- the persistent MLL kernel leaves it no SM to run on -- a peer store can.
+
+    Slots and totals are reused after RING steps: `next()` copies out any loss still un-waited after RING - 2 steps."""
+
+    RING = 8
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device)
+        self.slots = symm.empty(self.RING * self.world, dtype=torch.int64, device=self.device)
+        self.slots.zero_()                       # step numbers start at 1: a zeroed slot never matches
+        torch.cuda.synchronize(self.device)
+        self.handle = symm.rendezvous(self.slots, group)   # collective; every rank has zeroed its slots when it returns
+        self.handle.barrier()
+        torch.cuda.synchronize(self.device)
+        self.peers = int(self.handle.buffer_ptrs_dev)
+        self.totals = torch.zeros(self.RING, device=self.device)
+        self.seq = 0
+        self._pending = []       # weak references to the losses handed out, oldest first
+        self._launched = None    # event recorded after the newest step's launch
+
+    def next(self):
+        """-> the `exchange` tuple for ops.mll_step for the next step, and the loss object to hand to the caller;
+        call launched() right after the step has been enqueued."""
+        self.seq += 1
+        while self._pending and (self._pending[0]() is None or self._pending[0]()._seq <= self.seq - (self.RING - 2)):
+            old = self._pending.pop(0)()
+            if old is not None:
+                old._t = old.wait().clone()      # its totals entry is about to be reused
+        loss = _ExchangedLoss(self, self.seq)
+        self._pending.append(weakref.ref(loss))
+        return (self.peers, self.slots.data_ptr(), self.totals if self.seq > 1 else None, self.world, self.rank, self.RING,
+                self.seq), loss
+
+    def launched(self):
+        """The step of `next()` is enqueued on the current stream: the previous step's total is ordered behind it."""
+        ev = torch.cuda.Event()
+        ev.record()
+        for ref in self._pending:
+            l = ref()
+            if l is not None and l._seq == self.seq - 1 and l._t is None:
+                l._t, l._ev = self.totals[l._seq % self.RING], ev
+
+    def _total(self, loss):
+        """Newest step (no later kernel has summed it): gather on the current stream."""
+        self._pending = [r for r in self._pending if r() is not None and r() is not loss]
+        out = torch.empty(1, device=self.device)
+        _lib.check(_lib.load().volt_loss_gather(self.slots.data_ptr(), self.world, self.RING, loss._seq & 0xFFFFFFFF,
+                                                out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+                   "volt_loss_gather")
+        return out.reshape(())
+
+
+_exchange = {}   # device index -> LossExchange, or None once setting it up failed (NCCL all-reduce is used instead)
+
+
+def _loss_exchange(device):
+    """The peer-memory exchange for this device when the job is multi-rank and VOLT_LOSS_EXCHANGE is not "nccl"."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    if os.environ.get("VOLT_LOSS_EXCHANGE", "peer") == "nccl" or dist.get_backend() != "nccl":
+        return None
+    idx = torch.device(device).index
+    if idx not in _exchange:
+        try:
+            _exchange[idx] = LossExchange(device)
+        except Exception as e:   # no peer access / symmetric memory unavailable: all ranks fail alike
+            warnings.warn(f"volt_b200: peer-memory loss exchange unavailable ({e}); using an NCCL all-reduce on a side stream")
+            _exchange[idx] = None
+    return _exchange[idx]
+
+
 def mll_and_grad(x, vol, resid, raw_noise, jitter=1e-6, check=False):
     """One MLL + gradient evaluation for each of the B local series (train_utils.py:247-250 per series): ONE launch
     (plus the prefix-sum kernel) -- the likelihood's softplus transform, dMLL/draw_noise and the rank-local partial of the
@@ -99,10 +202,19 @@ def mll_and_grad(x, vol, resid, raw_noise, jitter=1e-6, check=False):
     x (T,), vol (B,T), resid (B,T) = log y - mean, raw_noise (B,).  Returns dict of CUDA tensors:
     mll (B,), draw_noise (B,) = dMLL/draw_noise, alpha (B,T) (dMLL/dmean = alpha/T), info (B,), scalars (B,16), and
     loss = -sum mll over ALL ranks as a PendingLoss (float(loss) / loss.wait())."""
-    out = ops.mll_step("vol", x, vol, resid, raw_noise, jitter=jitter, check=check)
+    ex = _loss_exchange(resid.device if torch.is_tensor(resid) and resid.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    if ex is not None:
+        desc, loss = ex.next()
+        out = ops.mll_step("vol", x, vol, resid, raw_noise, jitter=jitter, check=False, exchange=desc)
+        ex.launched()
+        if check:
+            ops._check_info(out["info"], out["scalars"][:, ops.S_JITTER], "exact MLL")
+    else:
+        out = ops.mll_step("vol", x, vol, resid, raw_noise, jitter=jitter, check=check)
+        loss = _async_loss_all_reduce(out["loss"])
     sc = out["scalars"]
-    return dict(mll=sc[:, S_MLL], draw_noise=sc[:, S_DRAW], alpha=out["alpha"], info=out["info"],
-                loss=_async_loss_all_reduce(out["loss"]), scalars=sc)
+    return dict(mll=sc[:, S_MLL], draw_noise=sc[:, S_DRAW], alpha=out["alpha"], info=out["info"], loss=loss, scalars=sc,
+                partial_loss=out["loss"])
 
 
 def train_noise(x, vol, logy, k=25, mean_func="ewma", train_iters=300, lr=0.1, raw_init=1e-5):

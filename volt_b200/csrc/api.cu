@@ -176,7 +176,8 @@ __global__ void noise_from_raw_kernel(const float* __restrict__ raw, int stride,
   if (b < B) noise[b] = noise_from_raw_dev(raw[(size_t)b * stride]);
 }
 __global__ void __launch_bounds__(256) raw_finish_kernel(const float* __restrict__ raw, int stride, const float* __restrict__ noise,
-                                                         int B, float* __restrict__ scalars, float* __restrict__ loss_out) {
+                                                         int B, float* __restrict__ scalars, float* __restrict__ loss_out,
+                                                         LossExchange ex) {
   __shared__ float red[32];
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) {
@@ -187,7 +188,17 @@ __global__ void __launch_bounds__(256) raw_finish_kernel(const float* __restrict
   }
   const float tot = block_sum(acc, red);
   if (threadIdx.x == 0 && loss_out) loss_out[0] = -tot;
+  if (ex.peers && threadIdx.x < 32) exchange_partial_warp(ex, -tot, threadIdx.x);
 }
+
+// rank-local sum of the partial losses the ranks pushed into this rank's slots for step `seq` (fixed rank order: every
+// rank gets the same bits).  A slot that never arrives (a peer that failed) ends the wait after ~2 s with NaN.
+__global__ void loss_gather_kernel(const unsigned long long* __restrict__ slots, int world, int ring, unsigned int seq,
+                                   float* __restrict__ out) {
+  const float tot = exchange_sum_warp(slots, world, ring, seq, threadIdx.x);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+__global__ void push_zero_kernel(LossExchange ex) { exchange_partial_warp(ex, 0.f, threadIdx.x); }
 
 // implementation switch for the batched MLL kernel: 1 = tcgen05 (default), 0 = SIMT fp32 (kept for A/B measurement)
 static int g_mll_impl = -1;
@@ -315,15 +326,53 @@ int volt_mll_grad_vol(const float* x, int x_batched, const float* vol, int vol_m
   return launch_mll_batched(p, ST(stream));
 }
 
+static int mll_step_impl(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
+                         int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                         float* loss_out, const LossExchange& ex, void* stream);
+
 int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
                           int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
                           float* loss_out, void* stream) {
+  return mll_step_impl(x, x_batched, vol, vol_mode, resid, raw_noise, raw_stride, B, T, jitter, max_tries, scalars, alpha, info, loss_out,
+                       LossExchange{}, stream);
+}
+
+int volt_mll_step_sharded(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
+                          int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                          float* loss_out, const void* peer_slot_ptrs, const void* local_slots, float* prev_totals, int world, int rank,
+                          int ring, unsigned int seq, void* stream) {
+  VOLT_REQUIRE(peer_slot_ptrs && world >= 1 && rank >= 0 && rank < world && ring >= 2,
+               "volt_mll_step_sharded: bad exchange description (world=%d rank=%d ring=%d)", world, rank, ring);
+  VOLT_REQUIRE(!prev_totals || local_slots, "volt_mll_step_sharded: exchange with prev_totals needs local_slots");
+  LossExchange ex;
+  ex.peers = reinterpret_cast<const unsigned long long*>(peer_slot_ptrs);
+  ex.mine = reinterpret_cast<const unsigned long long*>(local_slots);
+  ex.totals = prev_totals;
+  ex.world = world; ex.rank = rank; ex.ring = ring; ex.seq = seq;
+  return mll_step_impl(x, x_batched, vol, vol_mode, resid, raw_noise, raw_stride, B, T, jitter, max_tries, scalars, alpha, info, loss_out,
+                       ex, stream);
+}
+
+int volt_loss_gather(const void* local_slots, int world, int ring, unsigned int seq, float* out, void* stream) {
+  VOLT_REQUIRE(local_slots && out && world >= 1 && ring >= 2, "volt_loss_gather: bad arguments");
+  loss_gather_kernel<<<1, 32, 0, ST(stream)>>>(reinterpret_cast<const unsigned long long*>(local_slots), world, ring, seq, out);
+  return check_cuda(cudaGetLastError(), "loss_gather_kernel");
+}
+
+static int mll_step_impl(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
+                         int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
+                         float* loss_out, const LossExchange& ex, void* stream) {
   if (B == 0) {   // empty shard: the step's partial loss is 0
     if (loss_out) VOLT_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
+    if (ex.peers) {
+      push_zero_kernel<<<1, 32, 0, ST(stream)>>>(ex);
+      return check_cuda(cudaGetLastError(), "push_zero_kernel");
+    }
     return VOLT_OK;
   }
   VOLT_REQUIRE(x && vol && resid && raw_noise && scalars, "volt_mll_grad_vol_raw: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol_raw: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
+  VOLT_REQUIRE(!ex.peers || loss_out, "volt_mll_step_sharded: the exchange needs loss_out");
   cudaStream_t st = ST(stream);
   void* V = nullptr;
   int s = get_workspace((size_t)B * T * sizeof(float), &V, 1, st);
@@ -348,6 +397,7 @@ int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int v
     p.raw_stride = raw_stride;
     p.loss_out = loss_out;
     p.done_counter = (unsigned int*)aux;
+    p.ex = ex;
     return launch_mll_batched_tc(p, st);
   }
   float* noise = (float*)aux + 64;
@@ -359,7 +409,7 @@ int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int v
   p.V = (const float*)V;
   s = launch_mll_batched(p, st);
   if (s) return s;
-  raw_finish_kernel<<<1, 256, 0, st>>>(raw_noise, raw_stride, noise, B, scalars, loss_out);
+  raw_finish_kernel<<<1, 256, 0, st>>>(raw_noise, raw_stride, noise, B, scalars, loss_out, ex);
   return check_cuda(cudaGetLastError(), "raw_finish_kernel");
 }
 

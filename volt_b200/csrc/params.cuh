@@ -9,6 +9,55 @@ enum { MA_EWMA = 0, MA_DEWMA = 1, MA_TEWMA = 2, MA_MEANREVERT = 3, MA_GIVEN = 4 
 constexpr int NSCALARS = 16;
 constexpr int NSERIES = 8;  // floats per series handed to the rollout: u.u, u.z1, V[n-1], dx, jitter, 0, 0, 0
 
+// Series-sharded loss without a collective launch (volt_mll_step_sharded).  Every rank owns ring * world 64-bit slots in
+// peer-mapped memory; a slot word is {step number : 32 | float bits : 32}, self-contained, so plain system-scope stores and
+// loads suffice (no ordering against other data).  The last CTA of the step's kernel stores this rank's partial into slot
+// [seq % ring][rank] of EVERY rank's buffer and, when `totals` is given, sums the PREVIOUS step's slots of its own buffer
+// (they arrived while this step ran) into totals[(seq - 1) % ring] -- in rank order, so every rank gets the same bits.
+struct LossExchange {
+  const unsigned long long* peers;   // device array of `world` pointers, entry r = rank r's slots
+  const unsigned long long* mine;    // this rank's slots
+  float* totals;                     // ring floats, or nullptr (first step: no previous step to sum)
+  int world, rank, ring;
+  unsigned int seq;
+};
+
+// value of slot `src` once it carries step `seq`; NaN after ~2 s (a peer that never got there)
+__device__ __forceinline__ float exchange_wait_slot(const unsigned long long* src, unsigned int seq) {
+  for (long long spin = 0; spin < 10000000LL; ++spin) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    if ((unsigned int)(v >> 32) == seq) return __uint_as_float((unsigned int)v);
+    __nanosleep(200);
+  }
+  return __int_as_float(0x7fc00000);
+}
+
+// total of step `seq` from this rank's slots; called by one whole warp, result valid on every lane
+__device__ __forceinline__ float exchange_sum_warp(const unsigned long long* mine, int world, int ring, unsigned int seq, int lane) {
+  float tot = 0.f;
+  for (int base = 0; base < world; base += 32) {
+    float val = 0.f;
+    if (base + lane < world) val = exchange_wait_slot(mine + (size_t)(seq % (unsigned)ring) * world + base + lane, seq);
+    const int n = (world - base < 32) ? world - base : 32;
+    for (int i = 0; i < n; ++i) tot += __shfl_sync(0xffffffffu, val, i);
+  }
+  return tot;
+}
+
+// called by one whole warp at the very end of the step (value = this rank's partial, same on every lane)
+__device__ __forceinline__ void exchange_partial_warp(const LossExchange& e, float value, int lane) {
+  const unsigned long long v = ((unsigned long long)e.seq << 32) | (unsigned long long)__float_as_uint(value);
+  for (int r = lane; r < e.world; r += 32) {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(e.peers[r]) + (size_t)(e.seq % (unsigned)e.ring) * e.world + e.rank;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+  }
+  if (e.totals) {
+    const float tot = exchange_sum_warp(e.mine, e.world, e.ring, e.seq - 1u, lane);
+    if (lane == 0) e.totals[(e.seq - 1u) % (unsigned)e.ring] = tot;
+  }
+}
+
 struct MllParams {
   int kind, B, T, Tp, nb;
   const float* dense; long long dense_bstride; int ldd;
@@ -42,6 +91,7 @@ struct MllParams {
   // dependent and starts on a series as soon as its flag is raised -- pack_out (B, NSERIES): u.u, u.z1, V[n-1], dx, jitter;
   // series_flag[b] = 1 (release) once pack_out / info of series b are written
   float* pack_out; const float* pack_x; int* series_flag;
+  LossExchange ex;   // series-sharded job: push the partial loss to the peers (ex.peers != nullptr)
 };
 
 // [GPyTorch] GaussianLikelihood / GreaterThan(1e-4): noise = softplus(raw_noise) + 1e-4 (torch's softplus: beta 1, threshold 20)

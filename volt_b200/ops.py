@@ -195,10 +195,15 @@ def mll_grad(kind, x, gen, resid, noise, jitter=1e-6, max_tries=3, vol_mode=VOL_
     return dict(scalars=scal, alpha=alpha, info=info)
 
 
-def mll_step(kind, x, gen, resid, raw_noise, jitter=1e-6, max_tries=3, vol_mode=VOL_SIGMA, check=True, want_alpha=True):
+def mll_step(kind, x, gen, resid, raw_noise, jitter=1e-6, max_tries=3, vol_mode=VOL_SIGMA, check=True, want_alpha=True,
+             exchange=None):
     """The training step of the data model in one launch (volt_mll_grad_vol_raw): like mll_grad(kind="vol") but takes the
     RAW likelihood noise (train_utils.py:222) -- softplus + 1e-4 is applied in-kernel -- and additionally returns
-    scalars[:, S_DRAW] = dMLL/draw_noise and `loss` (1,) = -sum_b MLL_b of this batch (fixed summation order)."""
+    scalars[:, S_DRAW] = dMLL/draw_noise and `loss` (1,) = -sum_b MLL_b of this batch (fixed summation order).
+
+    exchange = (peer_slot_ptrs_dev, local_slots_ptr, prev_totals tensor | None, world, rank, ring, seq): series-sharded job
+    -- the kernel's last CTA also stores the partial into every rank's exchange buffer over peer memory and sums the
+    previous step's slots (volt_mll_step_sharded); batched.LossExchange builds it."""
     if kind != "vol":
         raise ValueError("mll_step: only the Volatility-kernel data model has a fused training step")
     dev = _dev()
@@ -226,9 +231,17 @@ def mll_step(kind, x, gen, resid, raw_noise, jitter=1e-6, max_tries=3, vol_mode=
     alpha = _empty((B, T), dev) if want_alpha else None
     info = _empty((B,), dev, torch.int32)
     loss = _empty((1,), dev)
-    _lib.check(lib.volt_mll_grad_vol_raw(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(raw), rstride, B, T, float(jitter),
-                                         int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), _stream()),
-               "volt_mll_grad_vol_raw")
+    if exchange is None:
+        _lib.check(lib.volt_mll_grad_vol_raw(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(raw), rstride, B, T, float(jitter),
+                                             int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), _stream()),
+                   "volt_mll_grad_vol_raw")
+    else:
+        peers, mine, totals, world, rank, ring, seq = exchange
+        _lib.check(lib.volt_mll_step_sharded(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(raw), rstride, B, T, float(jitter),
+                                             int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), int(peers),
+                                             int(mine) or None, _ptr(totals), int(world), int(rank), int(ring),
+                                             int(seq) & 0xFFFFFFFF, _stream()),
+                   "volt_mll_step_sharded")
     if check:
         _check_info(info, scal[:, S_JITTER], "exact MLL")
     return dict(scalars=scal, alpha=alpha, info=info, loss=loss)
