@@ -10,7 +10,7 @@ from volt_b200 import _lib  # noqa: E402
 _lib.LIB_PATH = os.environ.get("VOLT_PROF_LIB") or os.path.join(os.path.dirname(_lib.LIB_PATH), "libvolt_prof.so")
 from volt_b200 import batched, ops  # noqa: E402
 
-B, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024), 512
+B, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024), (int(sys.argv[2]) if len(sys.argv) > 2 else 400)
 x, vol, logy = batched.synth_series(B, T)
 _, resid = ops.ma_mean("ewma", logy.cuda(), 25, want_resid=True)
 raw = torch.full((B,), 1e-5).cuda()

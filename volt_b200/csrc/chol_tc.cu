@@ -246,7 +246,10 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
           const int gr = r_base + row;
           TICK(0);
           bool have;
-          if constexpr (TMA == 2) have = gemm_w2_worker<false>(c, tp, r_base, Tp, 0, R0, ch == 0);
+          float zacc[2] = {0.f, 0.f};   // TMA = 2, first chunk: partial sums of L[j, 0:R0] z (and z2), taken from the B tiles
+          if constexpr (TMA == 2)
+            have = gemm_w2_worker<false>(c, tp, r_base, Tp, 0, R0, ch == 0, (ch == 0 && rb) ? c.z : nullptr,
+                                         (ch == 0 && rb2) ? c.z2 : nullptr, zacc);
           else if constexpr (TMA == 1) have = gemm_tma<false>(c, tp, &tmA, &tmB, sq_row0, r_base, Tp, R0, 0, R0);
           else if constexpr (TRI) have = gemm_tc1<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
           else have = gemm_tc<false>(c, S, ld, r_base, Tp, R0, 0, R0, nullptr);
@@ -303,9 +306,9 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
             stage_linv_from_lit(c, LiT);
             if (rb) {
               const int cz = tid >> 2, part = tid & 3;
-              float a1 = 0.f, a2 = 0.f;
+              float a1 = zacc[0], a2 = zacc[1];
               const float* Lrow = S + (size_t)(R0 + cz) * ld;
-              for (int k = part * 4; k < R0; k += 16) {
+              for (int k = part * 4; k < (TMA == 2 ? 0 : R0); k += 16) {
                 const float4 lv = *reinterpret_cast<const float4*>(Lrow + k);
                 a1 = fmaf(lv.x, c.z[k], a1); a1 = fmaf(lv.y, c.z[k + 1], a1);
                 a1 = fmaf(lv.z, c.z[k + 2], a1); a1 = fmaf(lv.w, c.z[k + 3], a1);

@@ -706,8 +706,13 @@ __device__ __forceinline__ void bar_workers_tma() { asm volatile("bar.sync 3, 28
 
 // dep: the call reads global data written since the previous call with dep = true (first chunk of a block step: the
 // panel / inverse block column of the step before); the other chunks of a step only read older columns.
+// zv / z2v (phase A, first chunk of a block step): the B operand of this call is the block row L[j, 0:R0] that the forward
+// substitution z_j = Linv_jj (r_j - L[j, 0:R0] z[0:R0]) needs, and the thread that splits B[row][4 part .. 4 part + 3] of a
+// k-tile is exactly the (row, part) owner of that GEMV's partial sum: four FMAs per tile replace a second pass over the
+// block row in global memory (same accumulation order as that pass: bit-identical).
 template <bool PHASE_B>
-__device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, int k_lo, int k_hi, bool dep) {
+__device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, int k_lo, int k_hi, bool dep,
+                               const float* zv = nullptr, const float* z2v = nullptr, float* zacc = nullptr) {
   const int nk = (k_hi - k_lo) / 16;
   if (nk <= 0) return false;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -744,6 +749,19 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
     tmem_st8(c.tmem + lane_base + TM_PLO + (uint32_t)(16 * s + 8 * half_id), lo);
     const uint32_t off = swz64(tid >> 2, tid & 3);
     const float4 b = *reinterpret_cast<const float4*>(BH + off);
+    if (!PHASE_B && zv) {
+      const int k0 = k_lo + 16 * kt + 4 * (tid & 3);
+      const float4 zq = *reinterpret_cast<const float4*>(zv + k0);
+      float a1 = zacc[0];
+      a1 = fmaf(b.x, zq.x, a1); a1 = fmaf(b.y, zq.y, a1); a1 = fmaf(b.z, zq.z, a1); a1 = fmaf(b.w, zq.w, a1);
+      zacc[0] = a1;
+      if (z2v) {
+        const float4 z2q = *reinterpret_cast<const float4*>(z2v + k0);
+        float a2 = zacc[1];
+        a2 = fmaf(b.x, z2q.x, a2); a2 = fmaf(b.y, z2q.y, a2); a2 = fmaf(b.z, z2q.z, a2); a2 = fmaf(b.w, z2q.w, a2);
+        zacc[1] = a2;
+      }
+    }
     float4 l;
     l.x = b.x - __uint_as_float(__float_as_uint(b.x) & 0xffffe000u);
     l.y = b.y - __uint_as_float(__float_as_uint(b.y) & 0xffffe000u);
@@ -806,13 +824,15 @@ __device__ __forceinline__ void w2_mma_call(TmaPipe& tp, uint32_t tmem_u, uint32
   tp.g = g0 + (uint32_t)nk;
 }
 
-// A-generator for one accumulator row: s[q] <- A[gr][gc0 + q] - s[q], q = 0..31.  Fast path (no identity padding, on-the-fly
-// kernels): the 32 column values come from 8 broadcast LDS.128 of the staged prefix vector.
+// A-generator for one accumulator row: s[q] <- A[gr][gc0 + q] - s[q], q = 0..31.  On-the-fly kernels: the 32 column values
+// come from 8 broadcast LDS.128 of the staged prefix vector (zero beyond T); the identity padding of rows / columns >= T is
+// applied per entry only by the threads whose 32 entries touch it (T = 400 in Tp = 448: the last block row and column).
 __device__ __forceinline__ void gen_sub_row32(const MllParams& p, int b, int gr, int gc0, const float* Vs, float sc, float dadd,
                                               float (&s)[32]) {
-  if (p.kind != KIND_DENSE && p.T == p.Tp) {
+  if (p.kind != KIND_DENSE) {
     const float vr = Vs[gr];
     const bool vol = (p.kind == KIND_VOL);
+    const bool interior = (gr < p.T) && (gc0 + 32 <= p.T);
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
       const float4 cv = *reinterpret_cast<const float4*>(Vs + gc0 + 4 * q4);
@@ -822,6 +842,7 @@ __device__ __forceinline__ void gen_sub_row32(const MllParams& p, int b, int gr,
         const int gc = gc0 + 4 * q4 + e;
         float v = vol ? ((gc <= gr) ? c4[e] : vr) : sc * fminf(vr, c4[e]);
         if (gc == gr) v += dadd;
+        if (!interior && (gr >= p.T || gc >= p.T)) v = (gc == gr) ? 1.f : 0.f;
         s[4 * q4 + e] = v - s[4 * q4 + e];
       }
     }
