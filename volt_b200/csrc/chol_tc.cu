@@ -90,13 +90,20 @@ __device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtens
       if (!arrived) break;
     }
     for (int attempt = 0;; ++attempt) {
+      bool wait_ring = true;                               // the diagonal block of step 0 uses the ring region as scratch
       for (int j = 1; j < nb; ++j) {                       // block step 0 has no earlier columns: no GEMM call
         const int R0 = j * NB, nk = R0 / 16;
         const int nch = (Tp - R0 + CM - 1) / CM;
         for (int ch = 0; ch < nch; ++ch) {
-          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + R0 + ch * CM, sq_row0 + R0, 0, nk);
+          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + R0 + ch * CM, sq_row0 + R0, 0, nk, wait_ring, ch == 0, nk - 4);
           else w2_mma_call(tp, tmem_u, xb, nk);
+          wait_ring = (ch == 0);                           // ... and so does the first-chunk epilogue of every step
         }
+      }
+      if (is_tma && wait_ring) {                           // the last step's release (keeps the phase count in step)
+        if (elect_one()) mbar_wait(tp.ringfree, tp.rf_n & 1u);
+        __syncwarp();
+        ++tp.rf_n;
       }
       // the workers publish the outcome of the factorisation (first failing column or -1) between two CTA-wide barriers
       asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
@@ -111,7 +118,8 @@ __device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtens
         const int nch = (R0 + CM - 1) / CM;
         for (int ch = 0; ch < nch; ++ch) {
           const int m_base = ch * CM, nk = (R0 - m_base) / 16;
-          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + m_base, sq_row0 + R0, m_base, nk);
+          // the preamble of every step stages the inverse diagonal block through the ring region
+          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + m_base, sq_row0 + R0, m_base, nk, ch == 0, ch == 0, nk - 4);
           else w2_mma_call(tp, tmem_u, xb, nk);
         }
       }
@@ -167,7 +175,10 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
   tp.full = reinterpret_cast<uint64_t*>(c.red + 44);
   tp.done = tp.full + W_RING;
   tp.ready = tp.done + W_RING;
+  tp.ringfree = tp.ready + W_RING;
+  tp.depready = tp.ringfree + 1;
   tp.g = 0;
+  tp.rf_n = tp.dep_n = 0;
 #ifdef VOLT_PROFILE
   for (int i = 0; i < 8; ++i) tp.prof[i] = 0;
 #endif
@@ -176,6 +187,8 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
     mbar_init(c.bar + 1, 1);
     if constexpr (TMA != 0) {
       for (int i = 0; i < W_RING; ++i) { mbar_init(tp.full + i, 1); mbar_init(tp.done + i, 1); mbar_init(tp.ready + i, NT / 32); }
+      mbar_init(tp.ringfree, 1);
+      mbar_init(tp.depready, 1);
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
@@ -347,7 +360,9 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
 #pragma unroll
               for (int q = 0; q < 32; ++q) s[q] = 0.f;
             }
-            wsync();  // LiT / tmp / stash (aliasing X) are dead from here on; Linv operand staged
+            // LiT / tmp / stash (aliasing X) are dead from here on; Linv operand staged
+            if constexpr (TMA == 2) w2_release_ring(tp);
+            else wsync();
           }
           TICK(5);
           float o[32];
@@ -359,6 +374,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
             const int g0 = r_base + 32 * (warp & 3);
             if (!(ch == 0 && (warp & 3) < 2) && g0 < Tp) {
               if constexpr (TRI) store_block32_2p(reinterpret_cast<float*>(c.X) + warp * 640, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+              else if constexpr (TMA == 2) store_block32_bl(c.X + W_BL, warp, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
               else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
             }
           }
@@ -403,7 +419,8 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
           for (int cc = tid; cc < NB; ++cc) a = fmaf(LiT[tid * CLD + cc], c.z[R0 + cc], a);
           c.al[R0 + tid] += a;
         }
-        wsync();
+        if (TMA == 2 && i >= 1) w2_release_ring(tp);   // LiT (ring region) is dead: the producer may load this step's tiles
+        else wsync();
         const int nch = (R0 + CM - 1) / CM;
         for (int ch = 0; ch < nch; ++ch) {
           const int m_base = ch * CM;
@@ -427,6 +444,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
             const int g0 = m_base + 32 * (warp & 3);
             if (g0 < R0) {
               if constexpr (TRI) store_block32_2p(reinterpret_cast<float*>(c.X) + warp * 640, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+              else if constexpr (TMA == 2) store_block32_bl(c.X + W_BL, warp, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
               else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
             }
           }

@@ -526,7 +526,10 @@ struct TmaPipe {
   uint64_t* full;    // [W_RING] TMA landed
   uint64_t* done;    // [W_RING] MMAs of the tile that used the slot have completed
   uint64_t* ready;   // [W_RING] (control-warp instance) the workers have split the tile: one arrival per worker warp
+  uint64_t* ringfree;   // (control-warp instance) the workers no longer use the ring region as scratch (diagonal block, preamble)
+  uint64_t* depready;   // (control-warp instance) the global writes of the previous block step are visible to the async proxy
   uint32_t g;        // running k-tile counter of this CTA (slot = g % W_RING, use = g / W_RING)
+  uint32_t rf_n, dep_n;   // producer side: phases of ringfree / depready consumed so far
 #ifdef VOLT_PROFILE
   long long prof[8];
 #endif
@@ -699,6 +702,15 @@ __device__ bool gemm_tma(Ctx& c, TmaPipe& tp, const void* tmA, const void* tmB, 
 // full(t) implies that the MMAs of tile t - RING have completed (the producer waited for them), which is what makes slot,
 // TMEM stage and B lo tile t % RING free to be overwritten: the workers need no other wait inside the loop, and no barrier.
 // The control warps follow the same deterministic schedule of GEMM calls as the workers (chol_tc.cu: w2_control).
+//
+// Across calls the producer runs AHEAD of the workers: t counts k-tiles over the whole kernel, so while the workers are in
+// the epilogue of one call (TRSM, stores -- their scratch is the B-lo region, not the ring) the first RING tiles of the
+// next call are already landing.  Two things hold it back, each an mbarrier the workers arrive on:
+//     ringfree:  the ring region doubles as LiT | diagonal-block scratch in the first-chunk epilogue of a phase-A block step
+//                and in phase B's per-step preamble; one phase per such use, consumed before the next call's first load
+//     depready:  the first chunk of a block step reads the panel / inverse block column the step before wrote to global
+//                memory; the workers fence (fence.proxy.async.global) and arrive once per block step, and the producer waits
+//                before the first k-tile of the newest 64-column slab -- the older slabs (K ascending) are loaded before that
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
 }
@@ -718,11 +730,11 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int row = 32 * (w & 3) + lane, half_id = w >> 2;
   const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
-  // earlier global writes (panel stores, diagonal blocks) -> visible to the async proxy; the ring region may have been the
-  // epilogue's scratch.  The producer starts this call's loads after the barrier.
-  if (dep) fence_proxy_async_global();
-  fence_async_smem();
-  bar_workers_tma();
+  if (dep) {   // earlier global writes (panel stores, diagonal blocks) -> visible to the async proxy, then tell the producer
+    fence_proxy_async_global();
+    wsync();
+    if (tid == 0) mbar_arrive(tp.depready);
+  }
   const uint32_t g0 = tp.g;
   const bool row_ok = (a_row0 + row) < a_row_end;
   const int mb = (a_row0 + row) >> 6;
@@ -783,14 +795,24 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
   return true;
 }
 
-// TMA producer warp: every lane takes the call-start barrier, one elected lane issues the loads
-__device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const void* tmB, uint32_t xb, int row_a, int row_b, int k_lo, int nk) {
-  bar_workers_tma();
+// the workers' side of ringfree: every worker calls this right after its last access to the ring region as scratch
+__device__ __forceinline__ void w2_release_ring(TmaPipe& tp) {
+  fence_async_smem();
+  wsync();
+  if (threadIdx.x == 0) mbar_arrive(tp.ringfree);
+}
+
+// TMA producer warp, one elected lane issues the loads.  wait_ring: the workers used the ring region as scratch since the
+// previous call; dep: the k-tiles from n_indep on read what the previous block step wrote.
+__device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const void* tmB, uint32_t xb, int row_a, int row_b, int k_lo, int nk,
+                                            bool wait_ring, bool dep, int n_indep) {
   const uint32_t g0 = tp.g;
   if (elect_one()) {
+    if (wait_ring) mbar_wait(tp.ringfree, tp.rf_n & 1u);
     for (int kt = 0; kt < nk; ++kt) {
       const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
-      if (kt >= W_RING) mbar_wait(tp.done + s, ((g - W_RING) / W_RING) & 1u);    // MMAs of the slot's previous tile (this call)
+      if (dep && kt == n_indep) mbar_wait(tp.depready, tp.dep_n & 1u);
+      if (g >= W_RING) mbar_wait(tp.done + s, ((g - W_RING) / W_RING) & 1u);    // MMAs of the tile that used the slot before
       mbar_expect_tx(tp.full + s, W_SLOT);
       tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, k_lo + 16 * kt, row_a);
       tma_load_2d(tmB, xb + s * W_SLOT + HA_TILE, tp.full + s, k_lo + 16 * kt, row_b);
@@ -798,6 +820,8 @@ __device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const 
   }
   __syncwarp();
   tp.g = g0 + (uint32_t)nk;
+  if (wait_ring) ++tp.rf_n;
+  if (dep) ++tp.dep_n;
 }
 
 // MMA issuer warp
@@ -864,6 +888,30 @@ __device__ __forceinline__ void store_block32(float* xs, const float (&o)[32], f
   for (int i = 0; i < 8; ++i) {
     const int r = (lane >> 3) + 4 * i, ch = (lane & 7) * 4;
     *reinterpret_cast<float4*>(gdst + (size_t)r * ld + ch) = *reinterpret_cast<const float4*>(xs + r * 36 + ch);
+  }
+}
+
+// store_block32 for the control-warp instance: the transposition tile lives in the B-lo region of the ring map (free between
+// GEMM calls; the ring slots themselves may already be receiving the next call's tiles).  Warp w owns bytes [512 w, 512 w + 512)
+// of each of the W_BLN lo tiles -- exactly the bytes its own threads write when they split a B tile, so no other warp ever
+// touches them -- i.e. four pieces of 8 rows x 16 floats: the 32 x 32 block goes out in two passes of 16 columns.  The 16-byte
+// chunk of a row is XOR-swizzled with (row / 2) % 4: each 8-lane phase of the STS.128 and of the LDS.128 hits 8 bank groups.
+__device__ __forceinline__ void store_block32_bl(uint8_t* bl, int warp, const float (&o)[32], float* gdst, int ld, int lane) {
+  float* mine = reinterpret_cast<float*>(bl + 512 * warp);
+  const int wp = lane >> 3, wr = lane & 7, wsw = (wr >> 1) & 3;        // write: lane = row -> piece, row in piece
+  const int rr = lane >> 2, rc = lane & 3, rsw = (rr >> 1) & 3;        // read: 8 rows x 4 chunks per pass
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(mine + wp * (HB_TILE / 4) + wr * 16 + 4 * (q ^ wsw)) =
+          make_float4(o[16 * h + 4 * q], o[16 * h + 4 * q + 1], o[16 * h + 4 * q + 2], o[16 * h + 4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(gdst + (size_t)(8 * i + rr) * ld + 16 * h + 4 * rc) =
+          *reinterpret_cast<const float4*>(mine + i * (HB_TILE / 4) + rr * 16 + 4 * (rc ^ rsw));
+    __syncwarp();
   }
 }
 
