@@ -28,6 +28,9 @@ print(f"CTA 0 total: {tot / 1e6:.2f} M cycles for {-(-B // 444)} series")
 print("diagonal block (thread 0 = pivot warp): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
     ["pivot16 / LiT clear", "barrier after pivot", "panel solve", "trailing update", "inverse blocks"], dg)))
 tm = out["alpha"].reshape(-1)[20:28].cpu().tolist()
-print("gemm_tma (thread 0): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
-    ["call-start fence+sync", "issue (TMA wait-done, TMA, MMA) + loop", "wait TMA full", "wait MMA done(g-2)", "split + st", "fence + barrier",
-     "drain"], tm)))
+print("W2 worker (thread 0): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
+    ["call start (dep fence + barrier)", "wait full, first tile", "wait full, other tiles", "split + st + fence + arrive", "wait last done",
+     "calls (x1000)", "k-tiles (x1000)"], tm)))
+cw = out["alpha"].reshape(-1)[28:36].cpu().tolist()
+print("W2 control warps (CTA 0): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
+    ["MMA wait ready", "MMA issue + commit", "TMA wait ringfree", "TMA wait depready", "TMA wait done", "TMA issue"], cw)))

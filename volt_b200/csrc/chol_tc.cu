@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
     for (int i = 0; i < 12; ++i) p.alpha[i] = (float)seg[i];
     for (int i = 0; i < 8; ++i) { p.alpha[12 + i] = (float)g_diag_prof[i]; g_diag_prof[i] = 0; }
     if constexpr (TMA != 0) for (int i = 0; i < 8; ++i) p.alpha[20 + i] = (float)tp.prof[i];
+    if constexpr (TMA == 2) for (int i = 0; i < 8; ++i) { p.alpha[28 + i] = (float)g_w2_prof[i]; g_w2_prof[i] = 0; }
   }
 #endif
   tc_fence_before();

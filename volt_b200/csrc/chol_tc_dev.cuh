@@ -730,11 +730,18 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int row = 32 * (w & 3) + lane, half_id = w >> 2;
   const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+#ifdef VOLT_PROFILE
+  long long wt0 = clock64(), wt1;
+#define WTICK(i) do { if (tid == 0) { wt1 = clock64(); tp.prof[i] += wt1 - wt0; wt0 = wt1; } } while (0)
+#else
+#define WTICK(i) do { } while (0)
+#endif
   if (dep) {   // earlier global writes (panel stores, diagonal blocks) -> visible to the async proxy, then tell the producer
     fence_proxy_async_global();
     wsync();
     if (tid == 0) mbar_arrive(tp.depready);
   }
+  WTICK(0);
   const uint32_t g0 = tp.g;
   const bool row_ok = (a_row0 + row) < a_row_end;
   const int mb = (a_row0 + row) >> 6;
@@ -744,6 +751,7 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
     const uint8_t* BH = RAW + HA_TILE;
     uint8_t* BL = c.X + W_BL + s * HB_TILE;
     mbar_wait(tp.full + s, (g / W_RING) & 1u);   // (probing the next tile's barrier early with test_wait was measured: +2 %)
+    WTICK(kt == 0 ? 1 : 2);
     uint32_t hi[8], lo[8];
     const bool live = row_ok && !(PHASE_B && ((k_lo + 16 * kt) >> 6) < mb);
 #pragma unroll
@@ -785,6 +793,7 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tp.ready + s);
+    WTICK(3);
   }
   tp.g = g0 + (uint32_t)nk;
   {
@@ -792,8 +801,21 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
     mbar_wait(tp.done + (gl % W_RING), (gl / W_RING) & 1u);
   }
   tc_fence_after();
+  WTICK(4);
+#ifdef VOLT_PROFILE
+  if (tid == 0) { tp.prof[5] += 1; tp.prof[6] += nk; }
+#endif
   return true;
 }
+
+#ifdef VOLT_PROFILE
+static __device__ long long g_w2_prof[8];   // control warps of CTA 0: MMA wait ready | MMA issue | TMA wait ringfree | depready | done | issue
+#define CTICK(i) do { if (blockIdx.x == 0) { const long long _n = clock64(); g_w2_prof[i] += _n - ct0; ct0 = _n; } } while (0)
+#define CTICK0() long long ct0 = clock64()
+#else
+#define CTICK(i) do { } while (0)
+#define CTICK0() do { } while (0)
+#endif
 
 // the workers' side of ringfree: every worker calls this right after its last access to the ring region as scratch
 __device__ __forceinline__ void w2_release_ring(TmaPipe& tp) {
@@ -802,20 +824,27 @@ __device__ __forceinline__ void w2_release_ring(TmaPipe& tp) {
   if (threadIdx.x == 0) mbar_arrive(tp.ringfree);
 }
 
+// (Measured and rejected: the producer pulling the whole NEXT call's tiles into the L2 with cp.async.bulk.prefetch.tensor --
+// c2 1.64 -> 1.73 ms, c3 2.29 -> 2.83 ms: with 296 MB of scratch squares behind a 126 MB L2 the prefetched lines evict the
+// lines the other CTAs are about to re-read.)
 // TMA producer warp, one elected lane issues the loads.  wait_ring: the workers used the ring region as scratch since the
 // previous call; dep: the k-tiles from n_indep on read what the previous block step wrote.
 __device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const void* tmB, uint32_t xb, int row_a, int row_b, int k_lo, int nk,
                                             bool wait_ring, bool dep, int n_indep) {
   const uint32_t g0 = tp.g;
   if (elect_one()) {
+    CTICK0();
     if (wait_ring) mbar_wait(tp.ringfree, tp.rf_n & 1u);
+    CTICK(2);
     for (int kt = 0; kt < nk; ++kt) {
       const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
-      if (dep && kt == n_indep) mbar_wait(tp.depready, tp.dep_n & 1u);
+      if (dep && kt == n_indep) { mbar_wait(tp.depready, tp.dep_n & 1u); CTICK(3); }
       if (g >= W_RING) mbar_wait(tp.done + s, ((g - W_RING) / W_RING) & 1u);    // MMAs of the tile that used the slot before
+      CTICK(4);
       mbar_expect_tx(tp.full + s, W_SLOT);
       tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, k_lo + 16 * kt, row_a);
       tma_load_2d(tmB, xb + s * W_SLOT + HA_TILE, tp.full + s, k_lo + 16 * kt, row_b);
+      CTICK(5);
     }
   }
   __syncwarp();
@@ -828,9 +857,11 @@ __device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const 
 __device__ __forceinline__ void w2_mma_call(TmaPipe& tp, uint32_t tmem_u, uint32_t xb, int nk) {
   const uint32_t g0 = tp.g;
   if (elect_one()) {
+    CTICK0();
     for (int kt = 0; kt < nk; ++kt) {
       const uint32_t g = g0 + (uint32_t)kt, s = g % W_RING;
       mbar_wait(tp.ready + s, (g / W_RING) & 1u);
+      CTICK(0);
       tc_fence_after();
       const uint64_t dbh = make_desc64(xb + s * W_SLOT + HA_TILE), dbl = make_desc64(xb + W_BL + s * HB_TILE);
 #pragma unroll
@@ -842,6 +873,7 @@ __device__ __forceinline__ void w2_mma_call(TmaPipe& tp, uint32_t tmem_u, uint32
         umma_tf32_ts(tmem_u + TM_ACC0, ah, dbh + adv, 1u);
       }
       umma_commit(tp.done + s);
+      CTICK(1);
     }
   }
   __syncwarp();
