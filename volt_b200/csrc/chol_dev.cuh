@@ -248,6 +248,10 @@ __device__ __forceinline__ void pivot16_warp(float* D, float* LiT, float* I16p, 
 // line with broadcast LDS.128 instead of ten shuffles per step, MUFU.RCP on the chain and rsqrt + Newton off it -- was
 // measured in round 2: correct, but 6.7 k instead of 3.4 k cycles per block: with in-order issue the STS -> __syncwarp ->
 // LDS round trip of every step costs more than the shuffles it replaces.)
+// (Also measured in round 2 and dropped: a split form -- the pivot warp only factors (55 % of the instructions), the panel below
+// is solved by substitution, one thread per row, and the last warp inverts block p from shared memory while block p + 1 is
+// being factored.  The pivot routine went from 3.4 k to 2.2 k cycles but the substitution costs 1.1 k against 0.46 k for the
+// product with the inverse: diagonal block 22 k -> 20 k cycles alone, and no change at all on c2 / c3 / c5.)
 __device__ __forceinline__ float dotn(const float* a, const float* b, int n) {  // n multiple of 4, 16-byte aligned
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (int t = 0; t < n; t += 4) {
