@@ -34,3 +34,5 @@ print("W2 worker (thread 0): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip
 cw = out["alpha"].reshape(-1)[28:36].cpu().tolist()
 print("W2 control warps (CTA 0): " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(
     ["MMA wait ready", "MMA issue + commit", "TMA wait ringfree", "TMA wait depready", "TMA wait done", "TMA issue"], cw)))
+ex = out["alpha"].reshape(-1)[36:40].cpu().tolist()
+print("phase B detail: " + ", ".join(f"{n} {v / 1e3:.0f}k" for n, v in zip(["preamble (Dinv -> LiT, stage, tr, alpha)", "store of the call"], ex)))

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
   const int sq_row0 = (int)blockIdx.x * p.Tp;   // first row of this CTA's scratch square in the tensor maps
 
 #ifdef VOLT_PROFILE
-  long long seg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long seg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
 #endif
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
@@ -339,11 +339,26 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
                 c.tmp[NB + cz] = ((rb2 && R0 + cz < T) ? rb2[R0 + cz] : 0.f) - a2;
               }
               wsync();
-              if (tid < (has2 ? 2 : 1) * NB) {
-                const int cc = tid & 63, which = tid >> 6;
-                float zz = 0.f;
-                for (int k = 0; k <= cc; ++k) zz = fmaf(LiT[k * CLD + cc], c.tmp[which * NB + k], zz);
-                (which ? c.z2 : c.z)[R0 + cc] = zz;
+              {
+                // z_j = Linv_jj t: four threads per entry (k = part, part + 4, ...), combined by shuffles in a fixed order
+                float zz = 0.f, zz2 = 0.f;
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                  const int k = part + 4 * it;
+                  if (k <= cz) {
+                    const float lv = LiT[k * CLD + cz];
+                    zz = fmaf(lv, c.tmp[k], zz);
+                    if (has2) zz2 = fmaf(lv, c.tmp[NB + k], zz2);
+                  }
+                }
+                zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+                zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+                zz2 += __shfl_xor_sync(0xffffffffu, zz2, 1);
+                zz2 += __shfl_xor_sync(0xffffffffu, zz2, 2);
+                if (part == 0) {
+                  c.z[R0 + cz] = zz;
+                  if (has2) c.z2[R0 + cz] = zz2;
+                }
               }
             }
             if (row >= NB) {
@@ -399,6 +414,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
       for (int i = 0; i < nb; ++i) {
         const int R0 = i * NB;
         const float* Di = dinv + (size_t)i * NB * NB;
+        TICK(7);
         // bring the inverted diagonal block back into shared memory once (coalesced), then stage the TRSM operand and
         // take its own contribution to tr(A^-1) and alpha from there
         for (int idx = tid; idx < NB * NB / 4; idx += NT) {
@@ -414,13 +430,22 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
             tr_part = fmaf(v, v, tr_part);
           }
         }
-        if (tid < NB) {
+        {
+          // alpha_i += Linv_ii^T z_i: four threads per row (cc = part, part + 4, ...), combined by shuffles in a fixed order
+          const int ar = tid >> 2, part = tid & 3;
           float a = 0.f;
-          for (int cc = tid; cc < NB; ++cc) a = fmaf(LiT[tid * CLD + cc], c.z[R0 + cc], a);
-          c.al[R0 + tid] += a;
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int cc = part + 4 * it;
+            if (cc >= ar) a = fmaf(LiT[ar * CLD + cc], c.z[R0 + cc], a);
+          }
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          if (part == 0) c.al[R0 + ar] += a;
         }
         if (TMA == 2 && i >= 1) w2_release_ring(tp);   // LiT (ring region) is dead: the producer may load this step's tiles
         else wsync();
+        TICK(12);
         const int nch = (R0 + CM - 1) / CM;
         for (int ch = 0; ch < nch; ++ch) {
           const int m_base = ch * CM;
@@ -448,6 +473,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
               else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
             }
           }
+          TICK(13);
           if (m < R0) {
             float dot = 0.f;
 #pragma unroll
@@ -561,6 +587,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
     for (int i = 0; i < 8; ++i) { p.alpha[12 + i] = (float)g_diag_prof[i]; g_diag_prof[i] = 0; }
     if constexpr (TMA != 0) for (int i = 0; i < 8; ++i) p.alpha[20 + i] = (float)tp.prof[i];
     if constexpr (TMA == 2) for (int i = 0; i < 8; ++i) { p.alpha[28 + i] = (float)g_w2_prof[i]; g_w2_prof[i] = 0; }
+    for (int i = 0; i < 4; ++i) p.alpha[36 + i] = (float)seg[12 + i];
   }
 #endif
   tc_fence_before();

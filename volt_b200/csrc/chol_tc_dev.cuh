@@ -730,6 +730,9 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int row = 32 * (w & 3) + lane, half_id = w >> 2;
   const uint32_t lane_base = (uint32_t)(32 * (w & 3)) << 16;
+  // (Measured and rejected: warps 0-3 splitting the A tile and warps 4-7 the B tile, so that the two latency chains of a
+  // k-tile run side by side -- the workers' own time per tile fell from 340 to 270 cycles but the wait for full(t) grew by
+  // the same amount: the tile rate is set by the TMA -> split -> MMA -> done round trip over a 4-slot ring, c2 1.64 -> 1.73 ms.)
 #ifdef VOLT_PROFILE
   long long wt0 = clock64(), wt1;
 #define WTICK(i) do { if (tid == 0) { wt1 = clock64(); tp.prof[i] += wt1 - wt0; wt0 = wt1; } } while (0)
@@ -809,7 +812,9 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
 }
 
 #ifdef VOLT_PROFILE
-static __device__ long long g_w2_prof[8];   // control warps of CTA 0: MMA wait ready | MMA issue | TMA wait ringfree | depready | done | issue
+static __device__ long long g_w2_prof[8];   // (-DVOLT_PROFILE_CTRL: intrusive, +40 % on the chain) control warps of CTA 0: MMA wait ready | MMA issue | TMA wait ringfree | depready | done | issue
+#endif
+#ifdef VOLT_PROFILE_CTRL
 #define CTICK(i) do { if (blockIdx.x == 0) { const long long _n = clock64(); g_w2_prof[i] += _n - ct0; ct0 = _n; } } while (0)
 #define CTICK0() long long ct0 = clock64()
 #else
@@ -826,7 +831,7 @@ __device__ __forceinline__ void w2_release_ring(TmaPipe& tp) {
 
 // (Measured and rejected: the producer pulling the whole NEXT call's tiles into the L2 with cp.async.bulk.prefetch.tensor --
 // c2 1.64 -> 1.73 ms, c3 2.29 -> 2.83 ms: with 296 MB of scratch squares behind a 126 MB L2 the prefetched lines evict the
-// lines the other CTAs are about to re-read.)
+// lines the other CTAs are about to re-read.  A short look-ahead, 6 or 10 tiles inside the same call, changes nothing: 1.63 ms.)
 // TMA producer warp, one elected lane issues the loads.  wait_ring: the workers used the ring region as scratch since the
 // previous call; dep: the k-tiles from n_indep on read what the previous block step wrote.
 __device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const void* tmB, uint32_t xb, int row_a, int row_b, int k_lo, int nk,
