@@ -11,7 +11,8 @@
 // Products on the tensor pipe, per 128-row chunk (all "TN": both operands K-contiguous in the scratch):
 //   Phase A   S   = A[rows, j] - L[rows, 0:j] L[j, 0:j]^T          K = 64 j
 //             L[rows, j] = S Linv_jj^T                              K = 64   (TRSM by the inverted diagonal block)
-//   Phase B   G^T = U[0:i, 0:i] L[i, 0:i]^T                         K = 64 i (U = (L^-1)^T, upper triangle of the scratch)
+//   Phase B   G^T = U[0:i, 0:i] L[i, 0:i]^T                         K = 64 i (U = (L^-1)^T, upper triangle of the scratch;
+//             control-warp instance: kept as L^-1 IN PLACE of the dead rows of L, so that a series touches half a square)
 //             U[0:i, i] = -G^T Linv_ii^T                            K = 64
 // SIMT work that remains: the 64x64 diagonal potrf / trtri (chol_dev.cuh), the hi/lo split while staging operand
 // tiles, the forward substitution for z, and the reductions.
@@ -77,7 +78,8 @@ constexpr int W2_THREADS = NT + 64;
 // Control warps of the TMA = 2 instance: they walk the same deterministic schedule of GEMM calls as the workers (series loop,
 // psd_safe_cholesky attempts, phase A block steps x row chunks, phase B) and feed / issue every k-tile of every call.
 template <bool HOSTIN>
-__device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtensorMap* tmA, const CUtensorMap* tmB, int wu) {
+__device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmAt,
+                           int wu) {
   const int Tp = p.Tp, nb = p.nb;
   const uint32_t xb = s_u32(c.X), tmem_u = make_uniform(c.tmem);
   const int sq_row0 = (int)blockIdx.x * Tp;
@@ -119,7 +121,7 @@ __device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtens
         for (int ch = 0; ch < nch; ++ch) {
           const int m_base = ch * CM, nk = (R0 - m_base) / 16;
           // the preamble of every step stages the inverse diagonal block through the ring region
-          if (is_tma) w2_tma_call(tp, tmA, tmB, xb, sq_row0 + m_base, sq_row0 + R0, m_base, nk, ch == 0, ch == 0, nk - 4);
+          if (is_tma) w2_tma_call(tp, tmAt, tmB, xb, sq_row0, sq_row0 + R0, m_base, nk, ch == 0, ch == 0, nk - 4, true, m_base);
           else w2_mma_call(tp, tmem_u, xb, nk);
         }
       }
@@ -129,7 +131,8 @@ __device__ void w2_control(const MllParams& p, Ctx& c, TmaPipe& tp, const CUtens
 
 template <bool TRI, bool HOSTIN = false, int TMA = 0>
 __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
-    mll_batched_tc_kernel(MllParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+    mll_batched_tc_kernel(MllParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmAt) {
   static_assert(!(TRI && TMA), "the TMA instances are two-CTA instances");
   static_assert(!(HOSTIN && TMA == 1), "the host-buffer entry uses the register-staged or the control-warp instance");
   constexpr bool PARK = TRI || TMA != 0;   // chunk-0 panel rows wait in the accumulator columns during the diagonal factorisation
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
       mbar_init(tp.depready, 1);
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      if constexpr (TMA == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAt) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
   if constexpr (TMA == 2) {
     const int wu = uniform_warp_id();
     if (wu >= NT / 32) {
-      w2_control<HOSTIN>(p, c, tp, &tmA, &tmB, wu);
+      w2_control<HOSTIN>(p, c, tp, &tmA, &tmB, &tmAt, wu);
       tc_fence_before();
       __syncthreads();   // pairs with the workers' barrier before the TMEM deallocation
       return;
@@ -312,7 +316,8 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
               // TMA instance: the diagonal block of the scratch holds the block of U = (L^-1)^T instead of L_jj (nothing reads
               // L_jj from the scratch again; the launcher keeps callers that want L out of this instance), so that phase B's
               // operand tiles are plain rectangles of the scratch
-              S[(size_t)(R0 + r) * ld + R0 + cc] = TMA != 0 ? LiT[r * CLD + cc] : ((cc <= r) ? c.Ct[r * CLD + cc] : 0.f);
+              S[(size_t)(R0 + r) * ld + R0 + cc] =
+                  TMA == 2 ? LiT[cc * CLD + r] : (TMA != 0 ? LiT[r * CLD + cc] : ((cc <= r) ? c.Ct[r * CLD + cc] : 0.f));
               dinv[((size_t)j * NB + r) * NB + cc] = LiT[r * CLD + cc];
             }
             if constexpr (PARK) wsync();   // D aliases the Linv operand: every read of L_jj precedes the staging
@@ -469,7 +474,13 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
             const int g0 = m_base + 32 * (warp & 3);
             if (g0 < R0) {
               if constexpr (TRI) store_block32_2p(reinterpret_cast<float*>(c.X) + warp * 640, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
-              else if constexpr (TMA == 2) store_block32_bl(c.X + W_BL, warp, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
+              else if constexpr (TMA == 2) {
+                // in place: U[m][R0 + c] = Linv[R0 + c][m] goes where L[i][m] was (dead once this step's calls have read their B
+                // tiles): the warp's 32 rows m are 128 contiguous bytes of row R0 + c -- no transposition tile needed
+                float* dst = S + (size_t)(R0 + c0) * ld + g0 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) dst[(size_t)q * ld] = o[q];
+              }
               else store_block32(reinterpret_cast<float*>(c.X) + warp * 1152, o, S + (size_t)g0 * ld + R0 + c0, ld, lane);
             }
           }
@@ -535,13 +546,14 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
       }
     }
     if (p.U_out && p.do_inverse) {
-      // (L^-1)^T: strictly-upper 64-blocks live in the scratch, the diagonal blocks in dinv (dinv[j][r][c] = Linv_jj[c][r])
+      // (L^-1)^T: strictly-upper 64-blocks live in the scratch (control-warp instance: transposed, in place of L), the
+      // diagonal blocks in dinv (dinv[j][r][c] = Linv_jj[c][r])
       float* Uo = p.U_out + (size_t)b * T * T;
       for (int idx = tid; idx < T * T; idx += NT) {
         const int r = idx / T, cc = idx - r * T;
         const int rb = r >> 6, cb = cc >> 6;
         float v = 0.f;
-        if (rb < cb) v = S[(size_t)r * ld + cc];
+        if (rb < cb) v = (TMA == 2) ? S[(size_t)cc * ld + r] : S[(size_t)r * ld + cc];
         else if (rb == cb) v = dinv[((size_t)rb * NB + (r & 63)) * NB + (cc & 63)];
         Uo[idx] = v;
       }
@@ -603,7 +615,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int encode_scratch_map(CUtensorMap* map, float* base, int Tp, long long rows, int box_rows) {
+static int encode_scratch_map(CUtensorMap* map, float* base, int Tp, long long rows, int box_rows, int box_cols = 16) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* f = nullptr;
@@ -616,10 +628,11 @@ static int encode_scratch_map(CUtensorMap* map, float* base, int Tp, long long r
   }
   const cuuint64_t dims[2] = {(cuuint64_t)Tp, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)Tp * sizeof(float)};
-  const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (Tp=%d rows=%lld box_rows=%d)", (int)r, Tp, rows, box_rows);
     return VOLT_ERR_CUDA;
@@ -646,16 +659,21 @@ static int launch_tc(MllParams p, cudaStream_t st, size_t smem, int per_sm) {
   if (s) return s;
   p.scratch = reinterpret_cast<float*>(ws);
   p.dinv = p.scratch + (size_t)grid * p.Tp * p.Tp;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmAt;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
+  memset(&tmAt, 0, sizeof(tmAt));
   if (TMA) {
     s = encode_scratch_map(&tmA, p.scratch, p.Tp, (long long)grid * p.Tp, 128);
     if (s) return s;
     s = encode_scratch_map(&tmB, p.scratch, p.Tp, (long long)grid * p.Tp, 64);
     if (s) return s;
+    if (TMA == 2) {   // phase B's A operand, stored transposed: 128 floats x 16 rows, dense
+      s = encode_scratch_map(&tmAt, p.scratch, p.Tp, (long long)grid * p.Tp, 16, 128);
+      if (s) return s;
+    }
   }
-  tc::mll_batched_tc_kernel<TRI, HOSTIN, TMA><<<grid, TMA == 2 ? tc::W2_THREADS : NT, smem, st>>>(p, tmA, tmB);
+  tc::mll_batched_tc_kernel<TRI, HOSTIN, TMA><<<grid, TMA == 2 ? tc::W2_THREADS : NT, smem, st>>>(p, tmA, tmB, tmAt);
   return check_cuda(cudaGetLastError(), "mll_batched_tc_kernel");
 }
 

@@ -757,15 +757,27 @@ __device__ bool gemm_w2_worker(Ctx& c, TmaPipe& tp, int a_row0, int a_row_end, i
     WTICK(kt == 0 ? 1 : 2);
     uint32_t hi[8], lo[8];
     const bool live = row_ok && !(PHASE_B && ((k_lo + 16 * kt) >> 6) < mb);
+    if constexpr (PHASE_B) {
+      // transposed tile (16 rows of k x 128 floats of m, no swizzle): this thread's row is a column of it, lanes read
+      // consecutive floats
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(RAW + swz64(row, 2 * half_id + q));
-      const float e[4] = {v.x, v.y, v.z, v.w};
+      for (int kk = 0; kk < 8; ++kk) {
+        const float v = *reinterpret_cast<const float*>(RAW + (8 * half_id + kk) * 512 + 4 * row);
+        const uint32_t u = live ? __float_as_uint(v) : 0u;
+        hi[kk] = u;
+        lo[kk] = __float_as_uint(__uint_as_float(u) - __uint_as_float(u & 0xffffe000u));
+      }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t u = live ? __float_as_uint(e[j]) : 0u;
-        hi[4 * q + j] = u;
-        lo[4 * q + j] = __float_as_uint(__uint_as_float(u) - __uint_as_float(u & 0xffffe000u));
+      for (int q = 0; q < 2; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(RAW + swz64(row, 2 * half_id + q));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t u = live ? __float_as_uint(e[j]) : 0u;
+          hi[4 * q + j] = u;
+          lo[4 * q + j] = __float_as_uint(__uint_as_float(u) - __uint_as_float(u & 0xffffe000u));
+        }
       }
     }
     tmem_st8(c.tmem + lane_base + TM_PHI + (uint32_t)(16 * s + 8 * half_id), hi);
@@ -834,8 +846,10 @@ __device__ __forceinline__ void w2_release_ring(TmaPipe& tp) {
 // lines the other CTAs are about to re-read.  A short look-ahead, 6 or 10 tiles inside the same call, changes nothing: 1.63 ms.)
 // TMA producer warp, one elected lane issues the loads.  wait_ring: the workers used the ring region as scratch since the
 // previous call; dep: the k-tiles from n_indep on read what the previous block step wrote.
+// a_t (phase B): the A operand is stored transposed (the inverse lives IN PLACE of L, see chol_tc.cu): tmA is then the map
+// with boxes of 128 floats x 16 rows, row_a the first row of the CTA's square and col_a the tile's first column.
 __device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const void* tmB, uint32_t xb, int row_a, int row_b, int k_lo, int nk,
-                                            bool wait_ring, bool dep, int n_indep) {
+                                            bool wait_ring, bool dep, int n_indep, bool a_t = false, int col_a = 0) {
   const uint32_t g0 = tp.g;
   if (elect_one()) {
     CTICK0();
@@ -847,7 +861,8 @@ __device__ __forceinline__ void w2_tma_call(TmaPipe& tp, const void* tmA, const 
       if (g >= W_RING) mbar_wait(tp.done + s, ((g - W_RING) / W_RING) & 1u);    // MMAs of the tile that used the slot before
       CTICK(4);
       mbar_expect_tx(tp.full + s, W_SLOT);
-      tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, k_lo + 16 * kt, row_a);
+      if (a_t) tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, col_a, row_a + k_lo + 16 * kt);
+      else tma_load_2d(tmA, xb + s * W_SLOT, tp.full + s, k_lo + 16 * kt, row_a);
       tma_load_2d(tmB, xb + s * W_SLOT + HA_TILE, tp.full + s, k_lo + 16 * kt, row_b);
       CTICK(5);
     }
