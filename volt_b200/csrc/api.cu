@@ -485,6 +485,46 @@ int volt_mll_grad_vol_host(const float* x, const float* vol, const float* resid,
     h_flags[1] = 0;
     h_flags[2] = 1;
   }
+  if (g_mll_impl < 0) {
+    const char* e = getenv("VOLT_MLL_IMPL");
+    g_mll_impl = (e && (e[0] == 's' || e[0] == '0')) ? 0 : 1;
+  }
+  // Direct form: when every buffer of the call is page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. torch's
+  // pin_memory()), it is already mapped into the device's address space: the kernel reads each series' 12 T input bytes
+  // straight from it at the start of that series (one PCIe round trip per series, hidden under the 0.4 ms the series
+  // takes) and writes the 64 output bytes (+ alpha) straight back.  No staging copies, no arrival flag, nothing before or
+  // after the launch but the final synchronisation.  VOLT_E2E_DIRECT=0 forces the staged pipeline below (also taken for
+  // pageable buffers, the SIMT implementation and the multi-CTA path of very long series).
+  {
+    static const int direct_env = [] { const char* e = getenv("VOLT_E2E_DIRECT"); return e ? atoi(e) : 1; }();
+    auto mapped = [](const void* h, void** d) -> bool {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+      *d = a.devicePointer;
+      return true;
+    };
+    void *mx, *mv, *mr, *mn, *ms, *ma = nullptr, *mi = nullptr;
+    if (direct_env && g_mll_impl && !(T >= 1536 && B <= 16) && mapped(x, &mx) && mapped(vol, &mv) && mapped(resid, &mr) &&
+        mapped(noise, &mn) && mapped(scalars, &ms) && (!alpha || mapped(alpha, &ma)) && (!info || mapped(info, &mi))) {
+      void* dinfo = mi;
+      if (!dinfo) {   // the kernel always records the status
+        int s = get_workspace((size_t)B * sizeof(int), &dinfo, 12, s_comp);
+        if (s) return s;
+      }
+      MllParams p = base_params(B, T, (const float*)mr, (const float*)mn, noise_stride, jitter, max_tries, (float*)ms, (float*)ma, (int*)dinfo);
+      p.kind = KIND_VOL;
+      p.vol_in = (const float*)mv;
+      p.x_in = (const float*)mx;
+      p.x_batched = 0;
+      p.vol_mode = VOLT_VOL_SIGMA;
+      p.stage_in = 1;
+      int s = launch_mll_batched_tc(p, s_comp);
+      if (s) return s;
+      VOLT_CUDA(cudaStreamSynchronize(s_comp));
+      return VOLT_OK;
+    }
+  }
   // every arena of this entry (staging, factor scratch, prefix sums) is keyed by the library's own compute stream, so the
   // call cannot race with work the caller has in flight on their streams through the device-pointer entry points
   void* ws = nullptr;

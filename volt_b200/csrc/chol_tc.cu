@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
   c.al = c.z + p.Tp;
   const bool has2 = (p.resid2 != nullptr);   // the second right-hand side (rollout prep) gets its own vector
   c.z2 = has2 ? c.al + p.Tp : c.z;
-  c.diagl = c.al + (has2 ? 2 : 1) * p.Tp;
+  float* rs_stage = c.al + (has2 ? 2 : 1) * p.Tp;   // p.stage_in: this series' residual, read from mapped host memory once
+  c.diagl = rs_stage + (p.stage_in ? p.Tp : 0);
   c.tmp = c.diagl + NB;
   c.red = c.tmp + 2 * NB;
   c.flag = reinterpret_cast<int*>(c.red + 32);
@@ -220,9 +221,25 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
 #endif
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (HOSTIN) {
-      const bool arrived = hostin_prologue((p.ready && b >= p.ready_from) ? p.ready : nullptr, p.ready_timeout, p.ready_spins,
-                                           p.x_in + (p.x_batched ? (size_t)b * T : 0), p.vol_in + (size_t)b * T, T, Tp, p.vol_mode, c.Vs,
-                                           c.flag);
+      const float* xs = p.x_in + (p.x_batched ? (size_t)b * T : 0);
+      const float* vs = p.vol_in + (size_t)b * T;
+      if (p.stage_in) {
+        // the inputs are the caller's pinned host buffers, mapped: ONE round trip over PCIe per series (12 T bytes, all
+        // threads), then the prefix sums and the residual are served from shared memory (z / al are free until the
+        // factorisation starts)
+        const float* rsrc = p.resid + (size_t)b * T;
+        for (int i = tid; i < T; i += NT) {
+          c.al[i] = __ldcs(xs + i);
+          c.z[i] = __ldcs(vs + i);
+          rs_stage[i] = __ldcs(rsrc + i);
+        }
+        wsync();
+        xs = c.al;
+        vs = c.z;
+      }
+      const bool arrived = hostin_prologue((p.ready && b >= p.ready_from) ? p.ready : nullptr, p.ready_timeout, p.ready_spins, xs, vs, T, Tp,
+                                           p.vol_mode, c.Vs, c.flag);
+      if (p.stage_in) wsync();   // warp 0 has read al / z before they are cleared below
       if constexpr (TMA == 2) {   // tell the control warps (w2_control)
         if (tid == 0) c.flag[1] = arrived ? 1 : 0;
         asm volatile("bar.sync 2, %0;" ::"n"(W2_THREADS) : "memory");
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
     const float sc = (p.kind == KIND_BM) ? p.scale[(size_t)b * p.scale_stride] : 1.f;
     const float dadd0 = p.raw_noise ? noise_from_raw_dev(p.raw_noise[(size_t)b * p.raw_stride])
                                     : (p.diag_add ? p.diag_add[(size_t)b * p.diag_stride] : 0.f);
-    const float* rb = p.resid ? p.resid + (size_t)b * T : nullptr;
+    const float* rb = (HOSTIN && p.stage_in) ? rs_stage : (p.resid ? p.resid + (size_t)b * T : nullptr);
     const float* rb2 = p.resid2 ? p.resid2 + (size_t)b * T : nullptr;
 
     int fail = 0;
@@ -701,7 +718,7 @@ static bool use_tma_default(int B, int T, int sms) {
 int launch_mll_batched_tc(MllParams p, cudaStream_t st) {
   p.Tp = (p.T + NB - 1) / NB * NB;
   p.nb = p.Tp / NB;
-  const size_t vec = sizeof(float) * (size_t)((p.resid2 ? 4 : 3) * p.Tp + NB + 2 * NB + 32 + 12 + 32);
+  const size_t vec = sizeof(float) * (size_t)(((p.resid2 ? 4 : 3) + (p.stage_in ? 1 : 0)) * p.Tp + NB + 2 * NB + 32 + 12 + 32);
   const size_t smem_total = 233472, smem_cta_reserved = 1024;   // sm_100: 228 KB per SM, 1 KB reserved per resident CTA
   // three resident CTAs per SM when the small shared-memory map fits three times (T <= 832); VOLT_TC_CTAS=2 / 3 forces the
   // double-buffered two-CTA / the three-CTA kernel (A/B timing)

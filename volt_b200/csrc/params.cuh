@@ -92,6 +92,7 @@ struct MllParams {
   // series_flag[b] = 1 (release) once pack_out / info of series b are written
   float* pack_out; const float* pack_x; int* series_flag;
   LossExchange ex;   // series-sharded job: push the partial loss to the peers (ex.peers != nullptr)
+  int stage_in;      // host-buffer entry on mapped pinned memory: x_in / vol_in / resid are host pointers -- one bulk read per series
 };
 
 // [GPyTorch] GaussianLikelihood / GreaterThan(1e-4): noise = softplus(raw_noise) + 1e-4 (torch's softplus: beta 1, threshold 20)
