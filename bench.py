@@ -360,6 +360,8 @@ def main():
     hi = torch.empty(B, dtype=torch.int32).pin_memory()
     e2e_loss = torch.zeros(1, device=dev)
 
+    e2e_direct = os.environ.get("VOLT_E2E_DIRECT", "1") != "0"
+
     def e2e_step():
         _lib.check(lib.volt_mll_grad_vol_host(hx.data_ptr(), hv.data_ptr(), hr.data_ptr(), hn.data_ptr(), 1, B, T, 1e-6, 3,
                                               hs.data_ptr(), None, hi.data_ptr()), "volt_mll_grad_vol_host")
@@ -476,8 +478,12 @@ def main():
         metric="MLL+grad evals/sec", value=value, unit="evals/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
         data="synthetic", config=config_of(desc, B, T), loss=loss,
-        e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=int((T + 2 * B * T + B) * 4 + (4 if world > 1 else 0)),
+        # direct form of the host entry (pinned buffers, default): every series reads x, vol and resid from mapped host memory
+        e2e=dict(value=e2e_value, unit="evals/s",
+                 h2d_bytes_per_step=int(((3 * B * T + B) if e2e_direct else (T + 2 * B * T + B)) * 4 + (4 if world > 1 else 0)),
                  d2h_bytes_per_step=int(B * 16 * 4 + B * 4 + (4 if world > 1 else 0)),
+                 transfer=("kernel reads / writes the caller's pinned host buffers (mapped) over PCIe" if e2e_direct
+                           else "staged: cudaMemcpyAsync H2D under the kernel + D2H"),
                  collective=("loss all-reduce inside the timed step" if world > 1 else "none (one rank)")),
         gpu_launches=int(launches),
         **({"per_rank": per_rank, "loss_exchange": type(out["loss"]).__name__} if world > 1 else {}),

@@ -218,6 +218,12 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
                  const float* resid_given, const float* mean_test, int use_theta, float theta, const float* latent, int joint,
                  float jitter, unsigned long long seed, float* samples, int* draw_info, int* series_info, void* stream);
 
+/* The base normals volt_rollout draws itself when eps == NULL (same Philox4x32-10 counters: key = seed, counter =
+ * (series, draw, step)), written as an eps tensor (B,S,H): volt_rollout(..., eps = this, ...) reproduces
+ * volt_rollout(..., eps = NULL, seed, ...) bit for bit.  Lets a caller re-run single flagged draws (draw_info bit 1, see
+ * above) with the numbers the kernel used.  joint: the mode flag of volt_rollout (the two modes index the generator differently). */
+int volt_rollout_normals(unsigned long long seed, int B, int S, int H, int joint, float* eps, void* stream);
+
 /* Forecast evaluation reductions over a rollout tensor, one pass over samples (B,S,H):
  *   ecdf[b,h]   = #{s : v < truth[b,h]} / S      voltron/option_utils.py:48-52 (ECDF; the caller passes log prices and the
  *                                                 log of the realised price) and the weather calibration notebook's

@@ -527,3 +527,45 @@ def test_loss_exchange_two_gpus():
                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "exchange_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "EXCHANGE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# in-kernel Philox normals as a tensor (volt_rollout_normals) and the per-draw fallback without explicit eps
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("joint", [False, True])
+def test_rollout_normals_reproduce_in_kernel_philox(joint):
+    """volt_rollout(eps = volt_rollout_normals(seed)) == volt_rollout(eps = NULL, seed), bit for bit, in both modes."""
+    from volt_b200 import _lib, ops
+    B, n, S, H, k, seed = 3, 96, 37, 11, 10, 1234
+    x, vol, logy = O.synth_series(B, n, seed=8)
+    g = torch.Generator().manual_seed(2)
+    pred_vol = 0.2 * torch.exp(0.2 * torch.randn(B, S, H, generator=g))
+    eps = torch.empty(B, S, H, device="cuda")
+    _lib.check(_lib.load().volt_rollout_normals(seed, B, S, H, int(joint), eps.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "volt_rollout_normals")
+    a, da, _ = ops.rollout(x, logy, vol, pred_vol, eps=None, seed=seed, mean_kind="ewma", k=k, joint=joint)
+    b, db, _ = ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind="ewma", k=k, joint=joint)
+    assert torch.equal(a, b) and torch.equal(da, db)
+    z = eps.flatten().double().cpu()
+    assert abs(float(z.mean())) < 0.1 and abs(float(z.std()) - 1.0) < 0.1
+
+
+@pytest.mark.gpu
+def test_rollout_per_draw_fallback_with_in_kernel_philox():
+    """The per-draw psd_safe_cholesky fallback (voltron/rollout_utils.py:35) no longer needs explicit base normals: with the
+    in-kernel generator the flagged draw is re-run with the regenerated numbers, so both forms agree bit for bit."""
+    from volt_b200 import _lib, ops
+    n, S, H, k, seed = 40, 5, 4, 10, 77
+    x, vol, logy = O.synth_series(1, n, seed=31)
+    g = torch.Generator().manual_seed(9)
+    pred_vol = 0.2 * torch.exp(0.1 * torch.randn(1, S, H, generator=g))
+    pred_vol[0, 2, 1] = 0.0                                                # duplicates a row of draw 2's matrix from step 2 on
+    eps = torch.empty(1, S, H, device="cuda")
+    _lib.check(_lib.load().volt_rollout_normals(seed, 1, S, H, 0, eps.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "volt_rollout_normals")
+    a, da, sa = ops.rollout(x, logy, vol, pred_vol, eps=None, seed=seed, mean_kind="ewma", k=k, check=True)
+    b, db, _ = ops.rollout(x, logy, vol, pred_vol, eps=eps, mean_kind="ewma", k=k, check=True)
+    assert int(sa[0]) == 0 and int(da[0, 2]) & 8 and not int(da[0, 2]) & 5   # repaired, not failed
+    assert torch.equal(a, b) and torch.equal(da, db)
+    assert bool(torch.isfinite(a).all())

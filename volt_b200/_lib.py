@@ -48,6 +48,7 @@ _SIGS = {
     "volt_mvn_sample": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, c_void_p]),
     "volt_rollout": (c_int, [_fp, _fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _fp, _fp, _fp,
                              c_int, c_float, _fp, c_int, c_float, c_ulonglong, _fp, _fp, _fp, c_void_p]),
+    "volt_rollout_normals": (c_int, [c_ulonglong, c_int, c_int, c_int, c_int, _fp, c_void_p]),
     "volt_rollout_stats": (c_int, [_fp, c_int, c_int, c_int, _fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_void_p]),
     "volt_gpcv_rows": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_float, _fp, _fp, c_void_p]),
     "volt_gemm_nt": (c_int, [_fp, c_longlong, c_longlong, _fp, c_longlong, c_longlong, _fp, c_longlong, c_longlong, c_int, c_int,

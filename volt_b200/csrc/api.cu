@@ -786,6 +786,12 @@ int volt_rollout(const float* x, const float* logy, const float* vol, int vol_mo
   return launch_rollout(q, st);
 }
 
+int volt_rollout_normals(unsigned long long seed, int B, int S, int H, int joint, float* eps, void* stream) {
+  VOLT_REQUIRE(B >= 0 && S >= 0 && H >= 0 && (eps || (long long)B * S * H == 0), "volt_rollout_normals: bad arguments");
+  // series beyond 65535 are numbered on (b_offset + b) inside volt_rollout's chunks: one global numbering here
+  return launch_rollout_normals(seed, 0, B, S, H, joint, eps, ST(stream));
+}
+
 int volt_rollout_stats(const float* samples, int B, int S, int H, const float* truth, const float* strike, int exp_flag,
                        float* ecdf, float* mean, float* sd, float* nll, float* payoff, void* stream) {
   if (B == 0) return VOLT_OK;   // empty batch (e.g. an empty shard): nothing to do

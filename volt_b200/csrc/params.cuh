@@ -166,6 +166,7 @@ int launch_mll_batched_tc(MllParams p, cudaStream_t st);   // tcgen05 3xTF32 ten
 int mll_tc_resident_ctas(int T, int two_rhs);              // series in flight per launch of that kernel
 int launch_mll_large(const MllParams& p, int b, cudaStream_t st);  // multi-CTA path for one long series (chol_large.cu)
 int launch_rollout(RolloutParams p, cudaStream_t st);
+int launch_rollout_normals(unsigned long long seed, int b_offset, int B, int S, int H, int joint, float* out, cudaStream_t st);
 int launch_gemm_nt(const float* A, long long lda, long long a_bstride, const float* B, long long ldb, long long b_bstride, float* C,
                    long long ldc, long long c_bstride, int M, int N, int K, int batch, int mode, int tri, int max_ctas, cudaStream_t st);
 int launch_gpcv_rows(const float* chol_var, const float* W, const float* var_mean, const float* y, const float* gh_t, const float* gh_w,

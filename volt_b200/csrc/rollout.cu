@@ -398,6 +398,32 @@ int launch_ma_paths(const float* y, int S, int T, int k, const float* w, int kin
   return check_cuda(cudaGetLastError(), "ma_paths_kernel");
 }
 
+// The base normals the rollout kernel draws for (series, draw, step) when no eps is given -- the same Philox counters, so a
+// caller can re-run single draws (the per-draw psd_safe_cholesky fallback of volt_b200.ops.rollout) with the exact numbers
+// the in-kernel generator used.
+__global__ void __launch_bounds__(256) rollout_normals_kernel(unsigned long long seed, int b_offset, long long total, int S, int H, int joint,
+                                                              float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int h = (int)(i % H);
+  const long long bs = i / H;
+  const int s = (int)(bs % S), b = (int)(bs / S);
+  if (joint) {
+    out[i] = philox_normal(seed, (uint32_t)(b_offset + b), (uint32_t)s, (uint32_t)h);
+  } else {
+    float zq[4];
+    philox_normal4(seed, (uint32_t)(b_offset + b), (uint32_t)s, (uint32_t)(h >> 2), zq);
+    const int sel = h & 3;
+    out[i] = sel == 0 ? zq[0] : sel == 1 ? zq[1] : sel == 2 ? zq[2] : zq[3];
+  }
+}
+int launch_rollout_normals(unsigned long long seed, int b_offset, int B, int S, int H, int joint, float* out, cudaStream_t st) {
+  const long long total = (long long)B * S * H;
+  if (total == 0) return VOLT_OK;
+  rollout_normals_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(seed, b_offset, total, S, H, joint, out);
+  return check_cuda(cudaGetLastError(), "rollout_normals_kernel");
+}
+
 int launch_rollout(RolloutParams p, cudaStream_t st) {
   p.Hp = p.H | 1;
   int TS = 128;

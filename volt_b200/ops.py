@@ -413,7 +413,7 @@ def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0
     x (n,), logy (B,n) or (n,), vol (B,n) or (n,), pred_vol (B,S,H) or (S,H), eps like pred_vol or None (Philox).
     Returns samples (B,S,H) (CUDA), draw_info (B,S), series_info (B).  draw_info bits: 1 non-positive pivot in a draw's
     appended rows, 2 pred_cov needed jitter, 4 not PSD after the retries, 8 the draw was repaired by the per-draw
-    psd_safe_cholesky fallback (its whole matrix re-factored with jitter, step by step; needs explicit eps)."""
+    psd_safe_cholesky fallback (its whole matrix re-factored with jitter, step by step, with the same base normals)."""
     dev = _dev()
     xd = _f32(x, dev).reshape(-1)
     n = xd.numel()
@@ -449,7 +449,10 @@ def rollout(x, logy, vol, pred_vol, eps=None, mean_kind="ewma", k=25, mr_theta=0
                                         float(mr_theta), _ptr(mrl), _ptr(rg), _ptr(mt), use_theta,
                                         float(theta if theta is not None else 0.0), _ptr(lat), int(joint), float(jitter),
                                         int(seed), _ptr(out), _ptr(dinfo), _ptr(sinfo), _stream()), "volt_rollout")
-    if ep is not None and not joint and H > 1 and bool((dinfo & 1).any()):
+    if not joint and H > 1 and bool((dinfo & 1).any()):
+        if ep is None:   # in-kernel Philox: regenerate the very normals the kernel drew
+            ep = _empty((B, S, H), dev)
+            _lib.check(_lib.load().volt_rollout_normals(int(seed), B, S, H, 0, _ptr(ep), _stream()), "volt_rollout_normals")
         _redo_flagged_draws(out, dinfo, xd, ly, vd, vol_mode, pv, ep, kid, mean_kind, int(k), mr_theta, mrl, rg, mt, theta, lat, jitter)
     if check:
         if bool(sinfo.any()):
