@@ -135,23 +135,30 @@ int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int v
 /* volt_mll_grad_vol_raw for a series-sharded job (one process per GPU, each rank holds B of the series): the compute step and
  * the exchange of the loss in ONE kernel, no collective launch.  Every rank owns an exchange buffer of ring*world 64-bit
  * slots in peer-mapped memory; after the fixed-order sum, the kernel's last CTA stores {seq, -sum_b MLL_b} (one 64-bit
- * word) into slot [seq % ring][rank] of EVERY rank's buffer over NVLink, and -- when prev_totals is given -- adds up step
- * seq-1's slots of its own buffer (they arrived while this step ran), in rank order so every rank gets the same bits:
- * prev_totals[(seq-1) % ring] = total loss of step seq-1.
+ * word) into slot [seq % ring][rank] of EVERY rank's buffer over NVLink, and -- when prev_totals is given -- adds up the
+ * slots of step seq-lag of its own buffer (they arrived while the steps in between ran), in rank order so every rank gets
+ * the same bits: prev_totals[(seq-lag) % ring] = total loss of step seq-lag.  lag = 1 makes every step wait for the slowest
+ * rank's previous step; lag = 2 (volt_b200.batched) lets the ranks drift by a whole step, which absorbs their jitter.
  *   peer_slot_ptrs: DEVICE array of `world` pointers, entry r = rank r's buffer mapped into this process
  *                   (torch.distributed._symmetric_memory buffer_ptrs_dev, or cudaIpc / cuMem mappings); slots start zeroed.
- *   local_slots:    this rank's own buffer (needed with prev_totals).   prev_totals: ring floats or NULL (first step).
- *   seq:            step number, the same on every rank, 1, 2, 3, ...; ring >= 2 and no rank may run more than ring-1
- *                   steps ahead of another (prev_totals bounds it to 1).
+ *                   NULL: this call does not publish its partial (see volt_loss_push), it only sums step seq-lag.
+ *   local_slots:    this rank's own buffer (needed with prev_totals).   prev_totals: ring floats or NULL (seq <= lag).
+ *   seq:            step number, the same on every rank, 1, 2, 3, ...; 1 <= lag < ring, and no rank may run more than
+ *                   ring-1 steps ahead of another (prev_totals bounds it to lag).
  * Replaces the scalar the reference builds from the loss on one process (voltron/train_utils.py:249-250); the reference
  * has no multi-process path.  An empty shard (B = 0) pushes 0.
- * volt_loss_gather: total of step seq from this rank's slots (for the newest step, which no later kernel has summed yet);
+ * volt_loss_gather: total of step seq from this rank's slots (for the newest steps, which no later kernel has summed yet);
  * waits on the device, bounded (~2 s, then NaN), for slots that have not arrived.  out: 1 float. */
 int volt_mll_step_sharded(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
                           int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
-                          float* loss_out, const void* peer_slot_ptrs, const void* local_slots, float* prev_totals, int world, int rank,
-                          int ring, unsigned int seq, void* stream);
+                          float* loss_out, const void* peer_slot_ptrs, const void* local_slots, float* prev_totals, int lag, int world,
+                          int rank, int ring, unsigned int seq, void* stream);
 int volt_loss_gather(const void* local_slots, int world, int ring, unsigned int seq, float* out, void* stream);
+/* The push alone, from a value in device memory: stores {seq, *value} into slot [seq % ring][rank] of every rank's buffer
+ * (a one-warp kernel; small enough to run next to the resident CTAs of the next step).  With it a caller keeps remote
+ * stores out of the step kernel: volt_mll_step_sharded(peer_slot_ptrs = NULL, local_slots, prev_totals, ...) only sums, and
+ * this call, on another stream behind an event, publishes loss_out. */
+int volt_loss_push(const float* value, const void* peer_slot_ptrs, int world, int rank, int ring, unsigned int seq, void* stream);
 
 /* Same for the vol model BMGP (A = scale_b * min(x_i, x_j) + noise_b I)  -- voltron/train_utils.py:86-90,
  * voltron/models/BMGP.py:20-28.  x (T) shared grid. */

@@ -34,8 +34,9 @@ _SIGS = {
     "volt_mll_grad_vol_raw": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp,
                                       c_void_p]),
     "volt_mll_step_sharded": (c_int, [_fp, c_int, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp,
-                                      c_void_p, c_void_p, _fp, c_int, c_int, c_int, c_uint, c_void_p]),
+                                      c_void_p, c_void_p, _fp, c_int, c_int, c_int, c_int, c_uint, c_void_p]),
     "volt_loss_gather": (c_int, [c_void_p, c_int, c_int, c_uint, _fp, c_void_p]),
+    "volt_loss_push": (c_int, [_fp, c_void_p, c_int, c_int, c_int, c_uint, c_void_p]),
     "volt_mll_grad_bm": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_bm_inv": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp, _fp, c_void_p]),
     "volt_mll_grad_dense": (c_int, [_fp, c_longlong, c_int, _fp, _fp, c_int, c_int, c_int, c_float, c_int, _fp, _fp, _fp,

@@ -78,6 +78,8 @@ def _async_loss_all_reduce(partial):
 
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return PendingLoss(partial.reshape(()), None)
+    if os.environ.get("VOLT_LOSS_EXCHANGE") == "none":   # measurement only: every rank keeps its own partial (no exchange at all)
+        return PendingLoss(partial.reshape(()), None)
     dev = partial.device.index
     if dev not in _side:
         _side[dev] = [torch.cuda.Stream(device=dev), torch.empty(_RING, device=partial.device), 0]
@@ -113,14 +115,17 @@ class _ExchangedLoss(PendingLoss):
 class LossExchange:
     """The cross-rank sum of the step loss WITHOUT a collective launch: every rank owns a symmetric-memory
     buffer of RING x world 64-bit slots; the MLL kernel's last CTA stores {step number, partial} into slot
-    [step % RING][rank] of every rank's buffer over NVLink and adds up the previous step's slots of its own buffer
-    (volt_mll_step_sharded), so in a training loop the total of step s is simply there once step s + 1 has run; only the
-    newest step needs a tiny kernel that waits for its `world` slots (volt_loss_gather).  A separate NCCL kernel cannot
+    [step % RING][rank] of every rank's buffer over NVLink and adds up the slots of step - LAG of its own buffer
+    (volt_mll_step_sharded), so in a training loop the total of step s is simply there once step s + LAG has run; only the
+    newest LAG steps need a tiny kernel that waits for their `world` slots (volt_loss_gather).  LAG = 2 rather than 1: with
+    1 every step ends by waiting for the slowest rank's previous step and the ranks' jitter adds up (8 GPUs: 0.962 of linear);
+    with 2 they may drift by a whole step.  A separate NCCL kernel cannot
     overlap the next step here -- the persistent MLL kernel leaves it no SM to run on -- a peer store can.
 
     Slots and totals are reused after RING steps: `next()` copies out any loss still un-waited after RING - 2 steps."""
 
     RING = 8
+    LAG = 2      # the kernel of step s sums step s - LAG: ranks may drift by a whole step before one waits for another
 
     def __init__(self, device, group=None):
         import torch.distributed as dist
@@ -136,8 +141,13 @@ class LossExchange:
         self.handle.barrier()
         torch.cuda.synchronize(self.device)
         self.peers = int(self.handle.buffer_ptrs_dev)
-        self.totals = torch.zeros(self.RING, device=self.device)
+        self.totals = torch.zeros(self.RING + 1, device=self.device)   # (+1: wait-time counter of a -DVOLT_EXCHANGE_DEBUG build)
         self.seq = 0
+        # "kernel" (default): the step kernel's last CTA issues the remote stores itself.  "side": a one-warp kernel on a side
+        # stream does (volt_loss_push) -- measured at 8 GPUs: no difference (1.72 vs 1.78 ms per step, inside the run-to-run spread)
+        self.push_mode = os.environ.get("VOLT_LOSS_PUSH", "kernel")
+        self.side = torch.cuda.Stream(device=self.device) if self.push_mode == "side" else None
+        self._keep = []          # partial-loss buffers of the steps whose push may still be in flight
         self._pending = []       # weak references to the losses handed out, oldest first
         self._launched = None    # event recorded after the newest step's launch
 
@@ -145,22 +155,27 @@ class LossExchange:
         """-> the `exchange` tuple for ops.mll_step for the next step, and the loss object to hand to the caller;
         call launched() right after the step has been enqueued."""
         self.seq += 1
-        while self._pending and (self._pending[0]() is None or self._pending[0]()._seq <= self.seq - (self.RING - 2)):
+        while self._pending and (self._pending[0]() is None or self._pending[0]()._seq <= self.seq - (self.RING - self.LAG - 1)):
             old = self._pending.pop(0)()
             if old is not None:
                 old._t = old.wait().clone()      # its totals entry is about to be reused
         loss = _ExchangedLoss(self, self.seq)
         self._pending.append(weakref.ref(loss))
-        return (self.peers, self.slots.data_ptr(), self.totals if self.seq > 1 else None, self.world, self.rank, self.RING,
-                self.seq), loss
+        return (self.peers if self.side is None else 0, self.slots.data_ptr(), self.totals if self.seq > self.LAG else None, self.LAG,
+                self.world, self.rank, self.RING, self.seq), loss
 
-    def launched(self):
-        """The step of `next()` is enqueued on the current stream: the previous step's total is ordered behind it."""
+    def launched(self, partial=None):
+        """The step of `next()` is enqueued on the current stream: the total of the step LAG before it is ordered behind it."""
         ev = torch.cuda.Event()
         ev.record()
+        if self.side is not None:                # publish this step's partial from the side stream
+            self._keep = self._keep[-(self.RING - 1):] + [partial]
+            self.side.wait_event(ev)
+            _lib.check(_lib.load().volt_loss_push(partial.data_ptr(), self.peers, self.world, self.rank, self.RING,
+                                                  self.seq & 0xFFFFFFFF, self.side.cuda_stream), "volt_loss_push")
         for ref in self._pending:
             l = ref()
-            if l is not None and l._seq == self.seq - 1 and l._t is None:
+            if l is not None and l._seq == self.seq - self.LAG and l._t is None:
                 l._t, l._ev = self.totals[l._seq % self.RING], ev
 
     def _total(self, loss):
@@ -182,7 +197,7 @@ def _loss_exchange(device):
 
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return None
-    if os.environ.get("VOLT_LOSS_EXCHANGE", "peer") == "nccl" or dist.get_backend() != "nccl":
+    if os.environ.get("VOLT_LOSS_EXCHANGE", "peer") in ("nccl", "none") or dist.get_backend() != "nccl":
         return None
     idx = torch.device(device).index
     if idx not in _exchange:
@@ -206,7 +221,7 @@ def mll_and_grad(x, vol, resid, raw_noise, jitter=1e-6, check=False):
     if ex is not None:
         desc, loss = ex.next()
         out = ops.mll_step("vol", x, vol, resid, raw_noise, jitter=jitter, check=False, exchange=desc)
-        ex.launched()
+        ex.launched(out["loss"])
         if check:
             ops._check_info(out["info"], out["scalars"][:, ops.S_JITTER], "exact MLL")
     else:

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) raw_finish_kernel(const float* __restrict
   }
   const float tot = block_sum(acc, red);
   if (threadIdx.x == 0 && loss_out) loss_out[0] = -tot;
-  if (ex.peers && threadIdx.x < 32) exchange_partial_warp(ex, -tot, threadIdx.x);
+  if ((ex.peers || ex.totals) && threadIdx.x < 32) exchange_partial_warp(ex, -tot, threadIdx.x);
 }
 
 // rank-local sum of the partial losses the ranks pushed into this rank's slots for step `seq` (fixed rank order: every
@@ -199,6 +199,8 @@ __global__ void loss_gather_kernel(const unsigned long long* __restrict__ slots,
   if (threadIdx.x == 0) out[0] = tot;
 }
 __global__ void push_zero_kernel(LossExchange ex) { exchange_partial_warp(ex, 0.f, threadIdx.x); }
+// the push alone, from a value in device memory (volt_loss_push): a one-warp kernel that fits next to the resident step kernels
+__global__ void push_value_kernel(LossExchange ex, const float* value) { exchange_partial_warp(ex, *value, threadIdx.x); }
 
 // implementation switch for the batched MLL kernel: 1 = tcgen05 (default), 0 = SIMT fp32 (kept for A/B measurement)
 static int g_mll_impl = -1;
@@ -339,18 +341,29 @@ int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int v
 
 int volt_mll_step_sharded(const float* x, int x_batched, const float* vol, int vol_mode, const float* resid, const float* raw_noise,
                           int raw_stride, int B, int T, float jitter, int max_tries, float* scalars, float* alpha, int* info,
-                          float* loss_out, const void* peer_slot_ptrs, const void* local_slots, float* prev_totals, int world, int rank,
-                          int ring, unsigned int seq, void* stream) {
-  VOLT_REQUIRE(peer_slot_ptrs && world >= 1 && rank >= 0 && rank < world && ring >= 2,
-               "volt_mll_step_sharded: bad exchange description (world=%d rank=%d ring=%d)", world, rank, ring);
+                          float* loss_out, const void* peer_slot_ptrs, const void* local_slots, float* prev_totals, int lag, int world,
+                          int rank, int ring, unsigned int seq, void* stream) {
+  VOLT_REQUIRE(world >= 1 && rank >= 0 && rank < world && ring >= 2 && lag >= 1 && lag < ring,
+               "volt_mll_step_sharded: bad exchange description (world=%d rank=%d ring=%d lag=%d)", world, rank, ring, lag);
+  VOLT_REQUIRE(!prev_totals || seq > (unsigned)lag, "volt_mll_step_sharded: prev_totals needs seq > lag");
   VOLT_REQUIRE(!prev_totals || local_slots, "volt_mll_step_sharded: exchange with prev_totals needs local_slots");
   LossExchange ex;
   ex.peers = reinterpret_cast<const unsigned long long*>(peer_slot_ptrs);
   ex.mine = reinterpret_cast<const unsigned long long*>(local_slots);
   ex.totals = prev_totals;
-  ex.world = world; ex.rank = rank; ex.ring = ring; ex.seq = seq;
+  ex.world = world; ex.rank = rank; ex.ring = ring; ex.lag = lag; ex.seq = seq;
   return mll_step_impl(x, x_batched, vol, vol_mode, resid, raw_noise, raw_stride, B, T, jitter, max_tries, scalars, alpha, info, loss_out,
                        ex, stream);
+}
+
+int volt_loss_push(const float* value, const void* peer_slot_ptrs, int world, int rank, int ring, unsigned int seq, void* stream) {
+  VOLT_REQUIRE(value && peer_slot_ptrs && world >= 1 && rank >= 0 && rank < world && ring >= 2, "volt_loss_push: bad arguments");
+  LossExchange ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.peers = reinterpret_cast<const unsigned long long*>(peer_slot_ptrs);
+  ex.world = world; ex.rank = rank; ex.ring = ring; ex.lag = 1; ex.seq = seq;
+  push_value_kernel<<<1, 32, 0, ST(stream)>>>(ex, value);
+  return check_cuda(cudaGetLastError(), "push_value_kernel");
 }
 
 int volt_loss_gather(const void* local_slots, int world, int ring, unsigned int seq, float* out, void* stream) {
@@ -364,7 +377,7 @@ static int mll_step_impl(const float* x, int x_batched, const float* vol, int vo
                          float* loss_out, const LossExchange& ex, void* stream) {
   if (B == 0) {   // empty shard: the step's partial loss is 0
     if (loss_out) VOLT_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
-    if (ex.peers) {
+    if (ex.peers || ex.totals) {
       push_zero_kernel<<<1, 32, 0, ST(stream)>>>(ex);
       return check_cuda(cudaGetLastError(), "push_zero_kernel");
     }
@@ -372,7 +385,7 @@ static int mll_step_impl(const float* x, int x_batched, const float* vol, int vo
   }
   VOLT_REQUIRE(x && vol && resid && raw_noise && scalars, "volt_mll_grad_vol_raw: null pointer");
   VOLT_REQUIRE(B >= 1 && T >= 2, "volt_mll_grad_vol_raw: need B >= 1 and T >= 2 (got B=%d, T=%d)", B, T);
-  VOLT_REQUIRE(!ex.peers || loss_out, "volt_mll_step_sharded: the exchange needs loss_out");
+  VOLT_REQUIRE(!(ex.peers || ex.totals) || loss_out, "volt_mll_step_sharded: the exchange needs loss_out");
   cudaStream_t st = ST(stream);
   void* V = nullptr;
   int s = get_workspace((size_t)B * T * sizeof(float), &V, 1, st);

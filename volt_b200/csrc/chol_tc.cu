@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(TMA == 2 ? W2_THREADS : NT, TRI ? 3 : 2)
         p.loss_out[0] = -tot;
         *p.done_counter = 0u;   // ready for the next launch on this stream
       }
-      if (p.ex.peers && tid < 32) exchange_partial_warp(p.ex, -tot, tid);
+      if ((p.ex.peers || p.ex.totals) && tid < 32) exchange_partial_warp(p.ex, -tot, tid);
 
     }
   }

@@ -12,13 +12,14 @@ constexpr int NSERIES = 8;  // floats per series handed to the rollout: u.u, u.z
 // Series-sharded loss without a collective launch (volt_mll_step_sharded).  Every rank owns ring * world 64-bit slots in
 // peer-mapped memory; a slot word is {step number : 32 | float bits : 32}, self-contained, so plain system-scope stores and
 // loads suffice (no ordering against other data).  The last CTA of the step's kernel stores this rank's partial into slot
-// [seq % ring][rank] of EVERY rank's buffer and, when `totals` is given, sums the PREVIOUS step's slots of its own buffer
-// (they arrived while this step ran) into totals[(seq - 1) % ring] -- in rank order, so every rank gets the same bits.
+// [seq % ring][rank] of EVERY rank's buffer and, when `totals` is given, sums the slots of step seq - lag of its own buffer
+// (they arrived while the steps in between ran) into totals[(seq - lag) % ring] -- in rank order, so every rank gets the
+// same bits.  lag = 1 ties every rank to the slowest one step by step; lag = 2 lets them drift by a whole step.
 struct LossExchange {
   const unsigned long long* peers;   // device array of `world` pointers, entry r = rank r's slots
   const unsigned long long* mine;    // this rank's slots
-  float* totals;                     // ring floats, or nullptr (first step: no previous step to sum)
-  int world, rank, ring;
+  float* totals;                     // ring floats, or nullptr (no earlier step to sum yet)
+  int world, rank, ring, lag;        // the kernel of step seq sums step seq - lag (lag >= 1)
   unsigned int seq;
 };
 
@@ -48,13 +49,22 @@ __device__ __forceinline__ float exchange_sum_warp(const unsigned long long* min
 // called by one whole warp at the very end of the step (value = this rank's partial, same on every lane)
 __device__ __forceinline__ void exchange_partial_warp(const LossExchange& e, float value, int lane) {
   const unsigned long long v = ((unsigned long long)e.seq << 32) | (unsigned long long)__float_as_uint(value);
-  for (int r = lane; r < e.world; r += 32) {
+  for (int r = lane; e.peers && r < e.world; r += 32) {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(e.peers[r]) + (size_t)(e.seq % (unsigned)e.ring) * e.world + e.rank;
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
   }
   if (e.totals) {
-    const float tot = exchange_sum_warp(e.mine, e.world, e.ring, e.seq - 1u, lane);
-    if (lane == 0) e.totals[(e.seq - 1u) % (unsigned)e.ring] = tot;
+    const unsigned int old = e.seq - (unsigned)e.lag;
+#ifdef VOLT_EXCHANGE_DEBUG
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+    const float tot = exchange_sum_warp(e.mine, e.world, e.ring, old, lane);
+    if (lane == 0) e.totals[old % (unsigned)e.ring] = tot;
+#ifdef VOLT_EXCHANGE_DEBUG
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (lane == 0) e.totals[e.ring] += (float)(t1 - t0) * 1e-3f;   // microseconds spent waiting for the peers' slots (totals has ring + 1 entries)
+#endif
   }
 }
 

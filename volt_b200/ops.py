@@ -201,7 +201,7 @@ def mll_step(kind, x, gen, resid, raw_noise, jitter=1e-6, max_tries=3, vol_mode=
     RAW likelihood noise (train_utils.py:222) -- softplus + 1e-4 is applied in-kernel -- and additionally returns
     scalars[:, S_DRAW] = dMLL/draw_noise and `loss` (1,) = -sum_b MLL_b of this batch (fixed summation order).
 
-    exchange = (peer_slot_ptrs_dev, local_slots_ptr, prev_totals tensor | None, world, rank, ring, seq): series-sharded job
+    exchange = (peer_slot_ptrs_dev, local_slots_ptr, prev_totals tensor | None, lag, world, rank, ring, seq): series-sharded job
     -- the kernel's last CTA also stores the partial into every rank's exchange buffer over peer memory and sums the
     previous step's slots (volt_mll_step_sharded); batched.LossExchange builds it."""
     if kind != "vol":
@@ -236,10 +236,10 @@ def mll_step(kind, x, gen, resid, raw_noise, jitter=1e-6, max_tries=3, vol_mode=
                                              int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), _stream()),
                    "volt_mll_grad_vol_raw")
     else:
-        peers, mine, totals, world, rank, ring, seq = exchange
+        peers, mine, totals, lag, world, rank, ring, seq = exchange
         _lib.check(lib.volt_mll_step_sharded(_ptr(xd), xb, _ptr(g), vol_mode, _ptr(r), _ptr(raw), rstride, B, T, float(jitter),
-                                             int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), int(peers),
-                                             int(mine) or None, _ptr(totals), int(world), int(rank), int(ring),
+                                             int(max_tries), _ptr(scal), _ptr(alpha), _ptr(info), _ptr(loss), int(peers) or None,
+                                             int(mine) or None, _ptr(totals), int(lag), int(world), int(rank), int(ring),
                                              int(seq) & 0xFFFFFFFF, _stream()),
                    "volt_mll_step_sharded")
     if check:
