@@ -195,3 +195,77 @@ def test_bench_reference_arm_runs():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# bookkeeping of the multi-GPU loss exchange (volt_b200.batched.LossExchange) with the device parts replaced: which step's
+# total a loss object reads, when it is copied out of the ring, and that dropped losses cost nothing
+# ---------------------------------------------------------------------------------------------------------------------------
+class _FakeExchange:
+    """LossExchange with CPU tensors: the 'kernel' of step s writes totals[(s - LAG) % RING]; the gather returns the truth."""
+
+    def __new__(cls, truth):
+        from volt_b200 import batched
+
+        class Fake(batched.LossExchange):
+            def __init__(self, truth):
+                self.world, self.rank, self.device = 2, 0, torch.device("cpu")
+                self.slots = torch.zeros(self.RING * self.world, dtype=torch.int64)
+                self.peers, self.side, self.push_mode = 1, None, "kernel"
+                self.totals = torch.zeros(self.RING + 1)
+                self.seq, self._keep, self._pending, self._launched = 0, [], [], None
+                self.truth, self.gathers, self.events = truth, [], 0
+
+            def _record_event(self):
+                self.events += 1
+                return self.events
+
+            def _wait_event(self, ev):
+                assert ev <= self.events
+
+            def _total(self, loss):
+                self._pending = [r for r in self._pending if r() is not None and r() is not loss]
+                self.gathers.append(loss._seq)
+                return torch.tensor(self.truth[loss._seq])
+
+            def step(self):
+                desc, loss = self.next()
+                peers, mine, totals, lag, world, rank, ring, seq = desc
+                assert (totals is None) == (seq <= lag) and seq == self.seq
+                if totals is not None:                       # what volt_mll_step_sharded does on the device
+                    totals[(seq - lag) % ring] = self.truth[seq - lag]
+                self.launched()
+                return loss
+
+        return Fake(truth)
+
+
+def test_loss_exchange_bookkeeping_training_loop_pattern():
+    truth = {s: float(100 + s) for s in range(1, 60)}
+    ex = _FakeExchange(truth)
+    held = []
+    for s in range(1, 40):
+        held.append((s, ex.step()))
+        if len(held) > ex.LAG:                               # read the loss of LAG steps ago: never needs a gather
+            t, l = held.pop(0)
+            assert float(l.wait()) == truth[t]
+    assert ex.gathers == []
+    for t, l in held:                                        # the newest LAG steps do
+        assert float(l.wait()) == truth[t]
+    assert ex.gathers == [38, 39]
+
+
+def test_loss_exchange_bookkeeping_late_and_dropped_losses():
+    truth = {s: float(7 * s) for s in range(1, 80)}
+    ex = _FakeExchange(truth)
+    kept = {}
+    for s in range(1, 41):
+        loss = ex.step()
+        if s % 3 == 0:
+            kept[s] = loss                                   # held across many reuses of its ring entry; the others are dropped
+        if s == 20:
+            assert float(loss.wait()) == truth[20] and ex.gathers == [20]   # newest step, read at once: one gather
+    for s, l in kept.items():
+        assert float(l.wait()) == truth[s], s                # copied out before its entry was overwritten
+    assert ex.gathers == [20, 39]                            # 39 is one of the newest LAG steps; nothing else needed a kernel
+    assert len(ex._pending) <= ex.RING                       # dropped losses do not accumulate

@@ -106,8 +106,8 @@ class _ExchangedLoss(PendingLoss):
     def wait(self):
         if self._t is None:
             self._t = self._ex._total(self)
-        if self._ev is not None:                       # summed by the next step's kernel: order after that launch
-            torch.cuda.current_stream().wait_event(self._ev)
+        if self._ev is not None:                       # summed by a later step's kernel: order after that launch
+            self._ex._wait_event(self._ev)
             self._ev = None
         return self._t
 
@@ -118,11 +118,11 @@ class LossExchange:
     [step % RING][rank] of every rank's buffer over NVLink and adds up the slots of step - LAG of its own buffer
     (volt_mll_step_sharded), so in a training loop the total of step s is simply there once step s + LAG has run; only the
     newest LAG steps need a tiny kernel that waits for their `world` slots (volt_loss_gather).  LAG = 2 rather than 1: with
-    1 every step ends by waiting for the slowest rank's previous step and the ranks' jitter adds up (8 GPUs: 0.962 of linear);
-    with 2 they may drift by a whole step.  A separate NCCL kernel cannot
-    overlap the next step here -- the persistent MLL kernel leaves it no SM to run on -- a peer store can.
+    1 every step ends by waiting for the slowest rank's previous step; with 2 the ranks may drift by a whole step.  A
+    separate NCCL kernel cannot overlap the next step here -- the persistent MLL kernel leaves it no SM to run on -- a peer
+    store can.
 
-    Slots and totals are reused after RING steps: `next()` copies out any loss still un-waited after RING - 2 steps."""
+    Slots and totals are reused after RING steps: `next()` copies out any loss still un-waited RING - LAG - 1 steps later."""
 
     RING = 8
     LAG = 2      # the kernel of step s sums step s - LAG: ranks may drift by a whole step before one waits for another
@@ -164,10 +164,17 @@ class LossExchange:
         return (self.peers if self.side is None else 0, self.slots.data_ptr(), self.totals if self.seq > self.LAG else None, self.LAG,
                 self.world, self.rank, self.RING, self.seq), loss
 
-    def launched(self, partial=None):
-        """The step of `next()` is enqueued on the current stream: the total of the step LAG before it is ordered behind it."""
+    def _record_event(self):
         ev = torch.cuda.Event()
         ev.record()
+        return ev
+
+    def _wait_event(self, ev):
+        torch.cuda.current_stream().wait_event(ev)
+
+    def launched(self, partial=None):
+        """The step of `next()` is enqueued on the current stream: the total of the step LAG before it is ordered behind it."""
+        ev = self._record_event()
         if self.side is not None:                # publish this step's partial from the side stream
             self._keep = self._keep[-(self.RING - 1):] + [partial]
             self.side.wait_event(ev)
