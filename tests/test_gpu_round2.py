@@ -8,6 +8,8 @@
   norm-wise `relerr` of test_gpu_parity.py cannot see a wrong small entry;
 * a singular training block on which LAPACK does report failure, compared with the UNPATCHED oracle.
 """
+import math
+
 import pytest
 import torch
 
@@ -571,3 +573,46 @@ def test_rollout_per_draw_fallback_with_in_kernel_philox():
     assert int(sa[0]) == 0 and int(da[0, 2]) & 8 and not int(da[0, 2]) & 5   # repaired, not failed
     assert torch.equal(a, b) and torch.equal(da, db)
     assert bool(torch.isfinite(a).all())
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# psd_safe_cholesky retry on the control-warp TMA instance (T >= 448): the control warps repeat the schedule with the workers
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_jitter_retry_on_control_warp_instance():
+    """Two of six T = 512 series are pushed slightly indefinite (zero-vol segment, K - 1e-4 I): without jitter they report the
+    failing minor like cholesky_ex, with jitter 1e-3 exactly those two are re-factored (psd_safe_cholesky, per batch member)
+    and match fp64; the other four are bit-identical to a batch that never failed."""
+    from volt_b200 import ops
+    T, B = 512, 6
+    x = torch.arange(T) / 252.0
+    g = torch.Generator().manual_seed(0)
+    resid = 0.01 * torch.randn(B, T, generator=g)
+    Ks = []
+    for b in range(B):
+        vol = 0.2 * torch.exp(0.1 * torch.randn(T, generator=g))
+        if b in (1, 4):
+            vol[100:140] = 0.0
+        K = O.vol_kernel(x, vol)
+        Ks.append(K - 1e-4 * torch.eye(T) if b in (1, 4) else K)
+    K = torch.stack(Ks)
+    noise = torch.full((B,), 1e-3)
+    noise[1] = noise[4] = 0.0
+    bad = ops.mll_grad("dense", None, K.cuda(), resid.cuda(), noise.cuda(), jitter=0.0, check=False)
+    for b in range(B):
+        _, info_t = torch.linalg.cholesky_ex(K[b] + noise[b] * torch.eye(T))
+        assert (int(bad["info"][b]) > 0) == (int(info_t) > 0) == (b in (1, 4))
+    ok = ops.mll_grad("dense", None, K.cuda(), resid.cuda(), noise.cuda(), jitter=1e-3, check=False)
+    assert ok["info"].tolist() == [0] * B
+    assert [round(float(v), 6) for v in ok["scalars"][:, 7]] == [0.0, 1e-3, 0.0, 0.0, 1e-3, 0.0]
+    good = [0, 2, 3, 5]
+    ref = ops.mll_grad("dense", None, K[good].cuda(), resid[good].cuda(), noise[good].cuda(), jitter=1e-3, check=False)
+    assert torch.equal(ok["scalars"][good, :7], ref["scalars"][:, :7]) and torch.equal(ok["alpha"][good], ref["alpha"])
+    for b in (1, 4):
+        A = K[b].double() + float(ok["scalars"][b, 7]) * torch.eye(T, dtype=torch.float64)
+        L = torch.linalg.cholesky(A)
+        r = resid[b].double()
+        al = torch.cholesky_solve(r[:, None], L)[:, 0]
+        mll = (-0.5 * (r @ al) - L.diagonal().log().sum() - 0.5 * T * math.log(2 * math.pi)) / T
+        assert abs(float(ok["scalars"][b, 0]) - float(mll)) < 1e-5 * abs(float(mll))
+        assert relerr(ok["alpha"][b], al) < 2e-2            # condition number ~ 5e4 at this jitter
