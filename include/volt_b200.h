@@ -137,8 +137,8 @@ int volt_mll_grad_vol_raw(const float* x, int x_batched, const float* vol, int v
  * slots in peer-mapped memory; after the fixed-order sum, the kernel's last CTA stores {seq, -sum_b MLL_b} (one 64-bit
  * word) into slot [seq % ring][rank] of EVERY rank's buffer over NVLink, and -- when prev_totals is given -- adds up the
  * slots of step seq-lag of its own buffer (they arrived while the steps in between ran), in rank order so every rank gets
- * the same bits: prev_totals[(seq-lag) % ring] = total loss of step seq-lag.  lag = 1 makes every step wait for the slowest
- * rank's previous step; lag = 2 (volt_b200.batched) lets the ranks drift by a whole step, which absorbs their jitter.
+ * the same bits: prev_totals[(seq-lag) % ring] = total loss of step seq-lag.  lag = 1 (volt_b200.batched) keeps the ranks
+ * in lock step: no step ends before every rank has finished the one before it; lag = 2 lets them drift by a whole step.
  *   peer_slot_ptrs: DEVICE array of `world` pointers, entry r = rank r's buffer mapped into this process
  *                   (torch.distributed._symmetric_memory buffer_ptrs_dev, or cudaIpc / cuMem mappings); slots start zeroed.
  *                   NULL: this call does not publish its partial (see volt_loss_push), it only sums step seq-lag.

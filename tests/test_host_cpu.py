@@ -252,7 +252,7 @@ def test_loss_exchange_bookkeeping_training_loop_pattern():
     assert ex.gathers == []
     for t, l in held:                                        # the newest LAG steps do
         assert float(l.wait()) == truth[t]
-    assert ex.gathers == [38, 39]
+    assert ex.gathers == list(range(40 - ex.LAG, 40))
 
 
 def test_loss_exchange_bookkeeping_late_and_dropped_losses():
@@ -267,5 +267,6 @@ def test_loss_exchange_bookkeeping_late_and_dropped_losses():
             assert float(loss.wait()) == truth[20] and ex.gathers == [20]   # newest step, read at once: one gather
     for s, l in kept.items():
         assert float(l.wait()) == truth[s], s                # copied out before its entry was overwritten
-    assert ex.gathers == [20, 39]                            # 39 is one of the newest LAG steps; nothing else needed a kernel
+    # step 39 needs a gather only if it is one of the newest LAG steps (40 was the last one launched); nothing else does
+    assert ex.gathers == ([20, 39] if ex.LAG >= 2 else [20])
     assert len(ex._pending) <= ex.RING                       # dropped losses do not accumulate

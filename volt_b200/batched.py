@@ -117,15 +117,17 @@ class LossExchange:
     buffer of RING x world 64-bit slots; the MLL kernel's last CTA stores {step number, partial} into slot
     [step % RING][rank] of every rank's buffer over NVLink and adds up the slots of step - LAG of its own buffer
     (volt_mll_step_sharded), so in a training loop the total of step s is simply there once step s + LAG has run; only the
-    newest LAG steps need a tiny kernel that waits for their `world` slots (volt_loss_gather).  LAG = 2 rather than 1: with
-    1 every step ends by waiting for the slowest rank's previous step; with 2 the ranks may drift by a whole step.  A
-    separate NCCL kernel cannot overlap the next step here -- the persistent MLL kernel leaves it no SM to run on -- a peer
-    store can.
+    newest LAG steps need a tiny kernel that waits for their `world` slots (volt_loss_gather).  A separate NCCL kernel
+    cannot overlap the next step here -- the persistent MLL kernel leaves it no SM to run on -- a peer store can.
 
     Slots and totals are reused after RING steps: `next()` copies out any loss still un-waited RING - LAG - 1 steps later."""
 
     RING = 8
-    LAG = 2      # the kernel of step s sums step s - LAG: ranks may drift by a whole step before one waits for another
+    # The kernel of step s sums step s - LAG.  With 1 the ranks stay in lock step (a kernel cannot end before every rank has
+    # finished the step before it); 2 would let them drift by a whole step.  Measured at 8 GPUs (DESIGN.md section 4): lag 1
+    # 0.962 of linear in both runs, lag 2 between 0.84 and 0.96 over four -- the in-kernel wait is 2 us per step either way,
+    # so the default is the one with the steadier result.  VOLT_LOSS_LAG overrides it (same value on every rank).
+    LAG = max(1, min(4, int(os.environ.get("VOLT_LOSS_LAG", "1"))))
 
     def __init__(self, device, group=None):
         import torch.distributed as dist
