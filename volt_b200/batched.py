@@ -221,7 +221,8 @@ def _loss_exchange(device):
 def mll_and_grad(x, vol, resid, raw_noise, jitter=1e-6, check=False):
     """One MLL + gradient evaluation for each of the B local series (train_utils.py:247-250 per series): ONE launch
     (plus the prefix-sum kernel) -- the likelihood's softplus transform, dMLL/draw_noise and the rank-local partial of the
-    loss are produced by the kernel's epilogue (volt_mll_grad_vol_raw); the 4-byte all-reduce runs on a side stream.
+    loss are produced by the kernel's epilogue (volt_mll_grad_vol_raw); on more than one GPU the kernel also exchanges the
+    partial with the other ranks over peer memory (LossExchange; NCCL all-reduce on a side stream as the fallback).
 
     x (T,), vol (B,T), resid (B,T) = log y - mean, raw_noise (B,).  Returns dict of CUDA tensors:
     mll (B,), draw_noise (B,) = dMLL/draw_noise, alpha (B,T) (dMLL/dmean = alpha/T), info (B,), scalars (B,16), and
