@@ -8,12 +8,14 @@
 
 A "step" is one exact MLL + gradient evaluation for every series of the local batch (train_utils.py:247-250 per
 series): cumtrapz -> ONE kernel (fused build + potrf + forward substitution + trtri -> tr A^-1, alpha; likelihood
-transform, dMLL/draw_noise and the rank-local partial of the loss in its epilogue) -> scalar loss all-reduce (side
-stream).  The residual y - EWMA_k(y) is computed once outside the timed region in BOTH arms (it does not depend on the
+transform, dMLL/draw_noise and the rank-local partial of the loss in its epilogue; at N > 1 the same kernel pushes that
+partial into every rank's slot buffer over NVLink peer memory and sums the previous step's slots: no collective launch,
+DESIGN.md section 4).  The residual y - EWMA_k(y) is computed once outside the timed region in BOTH arms (it does not depend on the
 trained parameter; the reference recomputes it every iteration, 0.1 % of its step).
 `value` is timed with inputs resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks);
-`e2e` is the same metric through the host-buffer C-ABI call (H2D of x / vol / resid / noise and D2H of the per-series
-results inside the timed region; at N > 1 also the loss all-reduce).  Extra objects on the c2 line: `rollout` (c4 per-GPU
+`e2e` is the same metric through the host-buffer C-ABI call on pinned host buffers (the kernel reads x / vol / resid /
+noise from them over PCIe and writes the per-series results back, all inside the timed region; at N > 1 also an
+all-reduce of the loss); at N > 1 `per_rank` lists every rank's own step, kernel and enqueue time.  Extra objects on the c2 line: `rollout` (c4 per-GPU
 share), `long_series` (c5: one series of T = 8192), each with its own roofline and CPU baseline; `gpu_torch_baseline`
 (stock torch on the same GPU: what the reference's `.cuda()` path runs); `peaks` (incl. a TF32 cuBLAS GEMM measured in
 this run).  Other workloads (--workload c1|c3) are for profiling, not bench lines.
